@@ -1,0 +1,677 @@
+// fos_api.cu -- C ABI of libfos_b200.so (see include/fos.h): design handles, one-shot
+// operators, the power iteration and the proximal-gradient driver.  The host only launches
+// passes and polls a pinned copy of the control block; every numerical decision is taken on
+// the device (epilogue_kernels.cu).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fos_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void fos_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* fos_last_error(void) { return g_err; }
+extern "C" int fos_abi_version(void) { return FOS_ABI_VERSION; }
+
+extern "C" int fos_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int fos_device_info(int device, int* sm_count, size_t* total_bytes, size_t* free_bytes) {
+    FOS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FOS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    size_t f = 0, t = 0;
+    FOS_CUDA(cudaMemGetInfo(&f, &t));
+    if (total_bytes) *total_bytes = t;
+    if (free_bytes) *free_bytes = f;
+    return FOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// design lifetime
+// ------------------------------------------------------------------------------------------
+static inline int elem_size(int dtype) { return dtype == FOS_F64 ? 8 : 4; }
+
+static int design_common_init(fos_design* h, long long n, long long d, int dtype, int device) {
+    FOS_REQUIRE(n >= 1 && d >= 1, "design must have at least one row and one column (got %lld x %lld)", n, d);
+    FOS_REQUIRE(dtype == FOS_F64 || dtype == FOS_F32, "dtype must be FOS_F64 or FOS_F32");
+    FOS_REQUIRE(d <= 8192, "d = %lld exceeds the supported maximum of 8192 columns", d);
+    int ndev = fos_device_count();
+    if (ndev <= 0) {
+        fos_set_error("no CUDA device visible: libfos_b200 has no CPU fallback");
+        return FOS_ERR_CUDA;
+    }
+    FOS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
+    FOS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FOS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        fos_set_error("device %d is sm_%d%d; libfos_b200 contains sm_100a code only", device, prop.major,
+                      prop.minor);
+        return FOS_ERR_UNSUPPORTED;
+    }
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->n = n;
+    h->d = static_cast<int>(d);
+    h->dtype = dtype;
+    const int per16 = 16 / elem_size(dtype);
+    h->lda = static_cast<int>((d + per16 - 1) / per16 * per16);
+    h->ldv = static_cast<int>((d + 1) / 2 * 2);
+    FOS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    FOS_CUDA(cudaEventCreate(&h->ev0));
+    FOS_CUDA(cudaEventCreate(&h->ev1));
+    return FOS_OK;
+}
+
+static int design_alloc_work(fos_design* h) {
+    FOS_TRY(fos_grad_plan(h));
+    const size_t vb = static_cast<size_t>(h->ldv) * sizeof(double);
+    FOS_CUDA(cudaMalloc(&h->partial_g, static_cast<size_t>(h->n_parts) * vb));
+    FOS_CUDA(cudaMalloc(&h->partial_s, static_cast<size_t>(h->n_parts) * 2 * sizeof(double)));
+    FOS_CUDA(cudaMemsetAsync(h->partial_g, 0, static_cast<size_t>(h->n_parts) * vb, h->stream));
+    FOS_CUDA(cudaMemsetAsync(h->partial_s, 0, static_cast<size_t>(h->n_parts) * 2 * sizeof(double), h->stream));
+    double** vecs[4] = {&h->y, &h->xc, &h->xk, &h->g};
+    for (auto v : vecs) {
+        FOS_CUDA(cudaMalloc(v, vb));
+        FOS_CUDA(cudaMemsetAsync(*v, 0, vb, h->stream));
+    }
+    FOS_CUDA(cudaMalloc(&h->ctrl, sizeof(FosCtrl)));
+    FOS_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(FosCtrl), h->stream));
+    FOS_CUDA(cudaMallocHost(&h->ctrl_host, 4 * sizeof(FosCtrl)));
+    FOS_CUDA(cudaMallocHost(&h->vec_host, (2 * static_cast<size_t>(h->ldv) + 16) * sizeof(double)));
+    memset(h->ctrl_host, 0, 4 * sizeof(FosCtrl));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    return FOS_OK;
+}
+
+static void design_free(fos_design* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->owns_A && h->A) cudaFree(h->A);
+    if (h->owns_b && h->b) cudaFree(h->b);
+    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl};
+    for (void* p : bufs)
+        if (p) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->vec_host) cudaFreeHost(h->vec_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+#define FOS_TRY_FREE(h, expr)   \
+    do {                        \
+        int _s = (expr);        \
+        if (_s != FOS_OK) {     \
+            design_free(h);     \
+            return _s;          \
+        }                       \
+    } while (0)
+
+static int alloc_matrix(fos_design* h) {
+    const size_t bytes = static_cast<size_t>(h->n) * h->lda * elem_size(h->dtype);
+    cudaError_t e = cudaMalloc(&h->A, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fos_set_error("cannot allocate %.2f GB of HBM for A (%lld x %d)", bytes / 1e9, h->n, h->d);
+        return FOS_ERR_NOMEM;
+    }
+    h->owns_A = true;
+    FOS_CUDA(cudaMalloc(&h->b, static_cast<size_t>(h->n) * sizeof(double)));
+    h->owns_b = true;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
+                                 int64_t row_stride, int64_t col_stride, int device, fos_design** out) {
+    FOS_REQUIRE(A && b && out, "null pointer argument");
+    fos_design* h = new fos_design();
+    FOS_TRY_FREE(h, design_common_init(h, n, d, dtype, device));
+    FOS_TRY_FREE(h, alloc_matrix(h));
+    const size_t es = elem_size(dtype);
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaMemcpyAsync(h->b, b, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (col_stride == 1 && row_stride >= d) {
+            // C order (possibly with a row pitch): strided copy straight into the padded layout
+            if (h->lda != d)
+                FOS_CUDA(cudaMemsetAsync(h->A, 0, static_cast<size_t>(n) * h->lda * es, h->stream));
+            FOS_CUDA(cudaMemcpy2DAsync(h->A, static_cast<size_t>(h->lda) * es, A, static_cast<size_t>(row_stride) * es,
+                                       static_cast<size_t>(d) * es, static_cast<size_t>(n), cudaMemcpyHostToDevice,
+                                       h->stream));
+        } else if (row_stride == 1 && col_stride >= n) {
+            // Fortran order: upload column-major row chunks and transpose on the device
+            long long chunk = std::max<long long>(32, (256LL << 20) / (d * static_cast<long long>(es)));
+            chunk = std::min<long long>(chunk, n);
+            void* tmp = nullptr;
+            FOS_CUDA(cudaMalloc(&tmp, static_cast<size_t>(chunk) * d * es));
+            int st = FOS_OK;
+            for (long long r0 = 0; r0 < n && st == FOS_OK; r0 += chunk) {
+                const long long rows = std::min<long long>(chunk, n - r0);
+                cudaError_t ce = cudaMemcpy2DAsync(tmp, static_cast<size_t>(rows) * es,
+                                                   static_cast<const char*>(A) + static_cast<size_t>(r0) * es,
+                                                   static_cast<size_t>(col_stride) * es, static_cast<size_t>(rows) * es,
+                                                   static_cast<size_t>(d), cudaMemcpyHostToDevice, h->stream);
+                if (ce != cudaSuccess) {
+                    fos_set_error("column-major upload failed: %s", cudaGetErrorString(ce));
+                    st = FOS_ERR_CUDA;
+                    break;
+                }
+                st = fos_launch_repack(tmp, static_cast<char*>(h->A) + static_cast<size_t>(r0) * h->lda * es, rows,
+                                       h->d, h->lda, 0, 0, dtype, h->stream);
+            }
+            cudaStreamSynchronize(h->stream);
+            cudaFree(tmp);
+            if (st != FOS_OK) return st;
+        } else {
+            fos_set_error("unsupported strides (%lld, %lld): pass a C- or Fortran-contiguous matrix",
+                          static_cast<long long>(row_stride), static_cast<long long>(col_stride));
+            return FOS_ERR_UNSUPPORTED;
+        }
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        return FOS_OK;
+    };
+    FOS_TRY_FREE(h, body());
+    FOS_TRY_FREE(h, design_alloc_work(h));
+    *out = h;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_create_device(const void* A_dev, const double* b_dev, int64_t n, int64_t d, int dtype,
+                                        int64_t lda, int device, fos_design** out) {
+    FOS_REQUIRE(A_dev && b_dev && out, "null pointer argument");
+    fos_design* h = new fos_design();
+    FOS_TRY_FREE(h, design_common_init(h, n, d, dtype, device));
+    const int es = elem_size(dtype);
+    if (lda < d || (lda * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(A_dev) % 16) != 0) {
+        fos_set_error("borrowed matrix needs lda >= d, lda*elem %% 16 == 0 and a 16-byte aligned base");
+        design_free(h);
+        return FOS_ERR_INVALID;
+    }
+    h->lda = static_cast<int>(lda);
+    h->A = const_cast<void*>(A_dev);
+    h->b = const_cast<double*>(b_dev);
+    FOS_TRY_FREE(h, design_alloc_work(h));
+    *out = h;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_create_synthetic(int64_t n, int64_t d, int dtype, uint64_t seed, double noise_std,
+                                           double rho1, double rho2, int64_t row0, int device, fos_design** out) {
+    FOS_REQUIRE(out, "null pointer argument");
+    FOS_REQUIRE(fabs(rho1) <= 1.0 && fabs(rho2) <= 1.0, "correlations must lie in [-1, 1]");
+    fos_design* h = new fos_design();
+    FOS_TRY_FREE(h, design_common_init(h, n, d, dtype, device));
+    FOS_TRY_FREE(h, alloc_matrix(h));
+    FOS_TRY_FREE(h, fos_launch_synthetic(h, seed, noise_std, rho1, rho2, row0));
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        fos_set_error("synthetic generator failed: %s", cudaGetErrorString(e));
+        design_free(h);
+        return FOS_ERR_CUDA;
+    }
+    FOS_TRY_FREE(h, design_alloc_work(h));
+    *out = h;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_destroy(fos_design* h) {
+    design_free(h);
+    return FOS_OK;
+}
+
+extern "C" int fos_design_shape(const fos_design* h, int64_t* n, int64_t* d, int* dtype, int64_t* lda) {
+    FOS_REQUIRE(h, "null design");
+    if (n) *n = h->n;
+    if (d) *d = h->d;
+    if (dtype) *dtype = h->dtype;
+    if (lda) *lda = h->lda;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_pointers(fos_design* h, void** A_dev, double** b_dev) {
+    FOS_REQUIRE(h, "null design");
+    if (A_dev) *A_dev = h->A;
+    if (b_dev) *b_dev = h->b;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_download(fos_design* h, int64_t row0, int64_t rows, void* A_out, double* b_out) {
+    FOS_REQUIRE(h, "null design");
+    FOS_REQUIRE(row0 >= 0 && rows >= 0 && row0 + rows <= h->n, "row range out of bounds");
+    FOS_CUDA(cudaSetDevice(h->device));
+    const size_t es = elem_size(h->dtype);
+    if (A_out && rows > 0)
+        FOS_CUDA(cudaMemcpy2DAsync(A_out, static_cast<size_t>(h->d) * es,
+                                   static_cast<const char*>(h->A) + static_cast<size_t>(row0) * h->lda * es,
+                                   static_cast<size_t>(h->lda) * es, static_cast<size_t>(h->d) * es,
+                                   static_cast<size_t>(rows), cudaMemcpyDeviceToHost, h->stream));
+    if (b_out && rows > 0)
+        FOS_CUDA(cudaMemcpyAsync(b_out, h->b + row0, static_cast<size_t>(rows) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    return FOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers: vector upload/download through the pinned staging buffer
+// ------------------------------------------------------------------------------------------
+static int upload_vec(fos_design* h, double* dst_dev, const double* src_host, int slot) {
+    double* st = h->vec_host + static_cast<size_t>(slot) * h->ldv;
+    if (src_host)
+        memcpy(st, src_host, static_cast<size_t>(h->d) * sizeof(double));
+    else
+        memset(st, 0, static_cast<size_t>(h->d) * sizeof(double));
+    for (int c = h->d; c < h->ldv; ++c) st[c] = 0.0;
+    FOS_CUDA(cudaMemcpyAsync(dst_dev, st, static_cast<size_t>(h->ldv) * sizeof(double), cudaMemcpyHostToDevice,
+                             h->stream));
+    return FOS_OK;
+}
+
+static int run_oneshot(fos_design* h, int g_mode, int eop, double a1, double a2, int bits) {
+    FosHist none{};
+    FOS_TRY(fos_launch_grad(h, g_mode));
+    FOS_TRY(fos_launch_epilogue(h, eop, g_mode, none, a1, a2, bits));
+    return FOS_OK;
+}
+
+extern "C" int fos_grad(fos_design* h, const double* x, double alpha2, double* g_out, double* loss_out) {
+    FOS_REQUIRE(h && x, "null pointer argument");
+    FOS_CUDA(cudaSetDevice(h->device));
+    FOS_TRY(upload_vec(h, h->y, x, 0));
+    FOS_TRY(run_oneshot(h, GM_GRAD, EOP_FG, 0.0, alpha2, alpha2 != 0.0 ? 2 : 0));
+    FOS_CUDA(cudaMemcpyAsync(h->vec_host, h->g, static_cast<size_t>(h->ldv) * sizeof(double),
+                             cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    if (g_out) memcpy(g_out, h->vec_host, static_cast<size_t>(h->d) * sizeof(double));
+    if (loss_out) *loss_out = h->ctrl_host->out[0];
+    return FOS_OK;
+}
+
+extern "C" int fos_objective(fos_design* h, const double* x, int reg_bits, double alpha1, double alpha2,
+                             double* out) {
+    FOS_REQUIRE(h && x && out, "null pointer argument");
+    FOS_REQUIRE(reg_bits >= 0 && reg_bits <= 3, "reg_bits must be in 0..3");
+    FOS_CUDA(cudaSetDevice(h->device));
+    FOS_TRY(upload_vec(h, h->xc, x, 0));
+    FOS_TRY(run_oneshot(h, GM_DOT2, EOP_OBJ, alpha1, alpha2, reg_bits));
+    FOS_CUDA(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h->ctrl_host->out[0];
+    return FOS_OK;
+}
+
+extern "C" int fos_design_set_profile(fos_design* h, int enable) {
+    FOS_REQUIRE(h, "null design");
+    h->profile = enable != 0;
+    return FOS_OK;
+}
+
+extern "C" int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms_avg) {
+    FOS_REQUIRE(h && ms_avg && reps >= 1, "bad argument");
+    FOS_REQUIRE(mode > 0 && mode < 16, "mode must be a GM_* bit set");
+    FOS_REQUIRE(!(mode & GM_PROBE) || h->kern_kind == 1, "the streaming probe needs the streaming kernel (d > 512)");
+    FOS_CUDA(cudaSetDevice(h->device));
+    FOS_TRY(fos_launch_grad(h, mode));  // warm-up
+    FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps; ++i) FOS_TRY(fos_launch_grad(h, mode));
+    FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    FOS_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *ms_avg = ms / reps;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_lambda_max(fos_design* h, double* out) {
+    FOS_REQUIRE(h && out, "null pointer argument");
+    std::vector<double> zero(h->d, 0.0), g(h->d);
+    double loss;
+    FOS_TRY(fos_grad(h, zero.data(), 0.0, g.data(), &loss));  // g = -A^T b
+    double m = 0.0;
+    for (double v : g) m = std::max(m, fabs(v));
+    *out = m;
+    return FOS_OK;
+}
+
+// Estimated duration of one pass (used to size launch batches between polls).
+static int batch_size(const fos_design* h) {
+    const double bytes = static_cast<double>(h->n) * h->lda * elem_size(h->dtype);
+    const double t_pass = bytes / 5.0e12 + 12e-6;
+    int b = static_cast<int>(1.0e-3 / t_pass);
+    return std::max(1, std::min(b, 32));
+}
+
+// Launch (gradient, epilogue) pairs until the device reports completion.  `done` inspects a
+// pinned snapshot of the control block.  At most two batches are in flight.
+template <typename DoneFn>
+static int drive_passes(fos_design* h, int eop, const FosHist& hist, long long max_pairs, DoneFn done,
+                        long long* pairs_out) {
+    const int B = batch_size(h);
+    cudaEvent_t ev[2];
+    FOS_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    FOS_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    long long launched = 0;
+    int status = FOS_OK;
+    bool finished = false;
+    int batch = 0;
+    while (!finished && status == FOS_OK) {
+        if (batch >= 2) {
+            cudaError_t e = cudaEventSynchronize(ev[batch & 1]);
+            if (e != cudaSuccess) {
+                fos_set_error("solver loop failed: %s", cudaGetErrorString(e));
+                status = FOS_ERR_CUDA;
+                break;
+            }
+            if (done(h->ctrl_host[1 + (batch & 1)])) {
+                finished = true;
+                break;
+            }
+        }
+        if (launched >= max_pairs) {
+            // everything that can be needed is in flight: wait for the newest snapshot
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) {
+                fos_set_error("solver loop failed: %s", cudaGetErrorString(e));
+                status = FOS_ERR_CUDA;
+                break;
+            }
+            const FosCtrl& last = h->ctrl_host[1 + ((batch + 1) & 1)];
+            if (batch == 0 || done(last)) {
+                finished = true;
+            } else {
+                fos_set_error("solver did not finish within %lld passes (non-finite data?)", max_pairs);
+                status = FOS_ERR_INVALID;
+            }
+            break;
+        }
+        for (int i = 0; i < B && launched < max_pairs && status == FOS_OK; ++i, ++launched) {
+            const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
+            if (prof) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+            status = fos_launch_grad(h, -1);
+            if (prof) {
+                cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+                h->prof_used += 2;
+            }
+            if (status == FOS_OK) status = fos_launch_epilogue(h, eop, 0, hist, 0.0, 0.0, 0);
+        }
+        if (status != FOS_OK) break;
+        cudaError_t e = cudaMemcpyAsync(&h->ctrl_host[1 + (batch & 1)], h->ctrl, sizeof(FosCtrl),
+                                        cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[batch & 1], h->stream);
+        if (e != cudaSuccess) {
+            fos_set_error("solver loop failed: %s", cudaGetErrorString(e));
+            status = FOS_ERR_CUDA;
+            break;
+        }
+        ++batch;
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (status == FOS_OK && e != cudaSuccess) {
+        fos_set_error("solver loop failed: %s", cudaGetErrorString(e));
+        status = FOS_ERR_CUDA;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (pairs_out) *pairs_out = launched;
+    return status;
+}
+
+extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out,
+                              int* iters_out, float* gpu_ms_out) {
+    FOS_REQUIRE(h && v0 && L_out, "null pointer argument");
+    FOS_REQUIRE(n_iter >= 1, "n_iter must be >= 1");
+    FOS_CUDA(cudaSetDevice(h->device));
+    FosCtrl* c = h->ctrl_host;
+    memset(c, 0, sizeof(FosCtrl));
+    c->g_mode = GM_GRAD | GM_NOB;
+    c->phase = PH_DONE;
+    c->ptol = tol;
+    c->pit_max = n_iter;
+    c->L_prev = 0.0;
+    FOS_CUDA(cudaMemcpyAsync(h->ctrl, c, sizeof(FosCtrl), cudaMemcpyHostToDevice, h->stream));
+    FOS_TRY(upload_vec(h, h->y, v0, 0));
+    FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    FosHist none{};
+    long long pairs = 0;
+    FOS_TRY(drive_passes(h, EOP_POWER, none, n_iter, [](const FosCtrl& s) { return s.g_mode == GM_SKIP; }, &pairs));
+    FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    *L_out = c->L;
+    if (iters_out) *iters_out = c->pit;
+    if (gpu_ms_out) FOS_CUDA(cudaEventElapsedTime(gpu_ms_out, h->ev0, h->ev1));
+    return FOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// proximal-gradient engine
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t count) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            fos_set_error("cannot allocate %zu bytes of history on the device", count * sizeof(T));
+            return FOS_ERR_NOMEM;
+        }
+        return FOS_OK;
+    }
+};
+
+extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r) {
+    FOS_REQUIRE(h && p && r, "null pointer argument");
+    FOS_REQUIRE(p->scheme >= 0 && p->scheme <= 2, "unknown scheme %d", p->scheme);
+    FOS_REQUIRE(p->max_iter >= 0, "max_iter must be >= 0");
+    FOS_REQUIRE(p->step0 > 0.0 || p->max_iter == 0, "initial step must be positive");
+    FOS_REQUIRE(!p->backtracking || (p->eta > 0.0 && p->eta < 1.0), "eta must lie in (0, 1) for backtracking");
+    FOS_CUDA(cudaSetDevice(h->device));
+    const int K = p->max_iter;
+    const int d = h->d;
+    const bool want_hist = p->want_history != 0;
+    const bool want_obj = want_hist && p->scheme != FOS_SCHEME_ISTA;
+    const long long launches0 = h->launches;
+
+    // ---- per-solve device arrays
+    DevBuf<double> xh, oh, th, sh;
+    DevBuf<int> li;
+    DevBuf<float> gm, lm;
+    if (want_hist) FOS_TRY(xh.alloc(static_cast<size_t>(K + 1) * d));
+    FOS_TRY(oh.alloc(K));
+    FOS_TRY(th.alloc(K + 1));
+    FOS_TRY(sh.alloc(K));
+    FOS_TRY(li.alloc(K));
+    FOS_TRY(gm.alloc(K + 1));
+    FOS_TRY(lm.alloc(K));
+    FOS_CUDA(cudaMemsetAsync(li.p, 0, std::max(K, 1) * sizeof(int), h->stream));
+    FOS_CUDA(cudaMemsetAsync(gm.p, 0, (K + 1) * sizeof(float), h->stream));
+    FOS_CUDA(cudaMemsetAsync(lm.p, 0, std::max(K, 1) * sizeof(float), h->stream));
+    FOS_CUDA(cudaMemsetAsync(oh.p, 0, std::max(K, 1) * sizeof(double), h->stream));
+    FOS_CUDA(cudaMemsetAsync(sh.p, 0, std::max(K, 1) * sizeof(double), h->stream));
+    FosHist hist{};
+    hist.x_hist = want_hist ? xh.p : nullptr;
+    hist.obj_hist = oh.p;
+    hist.t_hist = th.p;
+    hist.step_hist = sh.p;
+    hist.ls_iters = li.p;
+    hist.grad_ms = gm.p;
+    hist.ls_ms = lm.p;
+
+    // ---- control block and start point
+    FosCtrl* c = h->ctrl_host;
+    memset(c, 0, sizeof(FosCtrl));
+    c->scheme = p->scheme;
+    c->backtracking = p->backtracking;
+    c->adaptive_restart = p->adaptive_restart;
+    c->want_hist = want_hist;
+    c->want_obj = want_obj;
+    c->max_iter = K;
+    c->obj_terms = p->obj_terms;
+    c->alpha1 = p->alpha1;
+    c->alpha2 = p->alpha2;
+    c->eta = p->eta;
+    c->tol = p->tol;
+    c->tol_ratio = p->tol_ratio;
+    c->restart_thr = p->restart_threshold;
+    c->delta = p->delta;
+    c->armijo_c = p->armijo_c;
+    c->phase = (K > 0) ? PH_GRAD : PH_DONE;
+    c->g_mode = (K > 0) ? GM_GRAD : GM_SKIP;
+    c->tau = p->step0;
+    c->trial_t = p->step0;
+    c->t_mom = 1.0;
+    c->prev_step = 0.0;
+    FOS_CUDA(cudaMemcpyAsync(h->ctrl, c, sizeof(FosCtrl), cudaMemcpyHostToDevice, h->stream));
+    FOS_TRY(upload_vec(h, h->y, p->x0, 0));
+    const size_t vb = static_cast<size_t>(h->ldv) * sizeof(double);
+    FOS_CUDA(cudaMemcpyAsync(h->xc, h->y, vb, cudaMemcpyDeviceToDevice, h->stream));
+    FOS_CUDA(cudaMemcpyAsync(h->xk, h->y, vb, cudaMemcpyDeviceToDevice, h->stream));
+    if (want_hist)
+        FOS_CUDA(cudaMemcpyAsync(xh.p, h->y, static_cast<size_t>(d) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 h->stream));
+    FOS_CUDA(cudaMemcpyAsync(th.p, &h->ctrl->tau, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+
+    // ---- the loop
+    long long max_pairs;
+    if (!p->backtracking && p->tol <= 0.0 && p->tol_ratio <= 0.0)
+        max_pairs = static_cast<long long>(K) + (want_obj ? 1 : 0);  // known exactly
+    else
+        max_pairs = static_cast<long long>(K) * 1200 + 8;  // tau underflows to 0 well before
+    h->prof_used = 0;
+    if (h->profile) {
+        const size_t want = std::min<size_t>(2 * static_cast<size_t>(max_pairs), 8192);
+        while (h->prof_ev.size() < want) {
+            cudaEvent_t e;
+            FOS_CUDA(cudaEventCreate(&e));
+            h->prof_ev.push_back(e);
+        }
+    }
+    FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    long long pairs = 0;
+    if (K > 0)
+        FOS_TRY(drive_passes(h, EOP_PG, hist, max_pairs, [](const FosCtrl& s) { return s.phase == PH_DONE; }, &pairs));
+    FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+
+    // ---- results
+    FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaMemcpyAsync(h->vec_host, h->xk, vb, cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    if (c->phase != PH_DONE && K > 0) {
+        fos_set_error("solver stopped in phase %d after %lld passes", c->phase, pairs);
+        return FOS_ERR_INVALID;
+    }
+    const int it = c->k;
+    if (r->x) memcpy(r->x, h->vec_host, static_cast<size_t>(d) * sizeof(double));
+    if (r->x_hist && want_hist)
+        FOS_CUDA(cudaMemcpy(r->x_hist, xh.p, static_cast<size_t>(it + 1) * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (r->obj_hist && it > 0) FOS_CUDA(cudaMemcpy(r->obj_hist, oh.p, it * sizeof(double), cudaMemcpyDeviceToHost));
+    if (r->t_hist) FOS_CUDA(cudaMemcpy(r->t_hist, th.p, (it + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (r->step_hist && it > 0) FOS_CUDA(cudaMemcpy(r->step_hist, sh.p, it * sizeof(double), cudaMemcpyDeviceToHost));
+    if (r->ls_iters && it > 0) FOS_CUDA(cudaMemcpy(r->ls_iters, li.p, it * sizeof(int), cudaMemcpyDeviceToHost));
+    if (r->grad_ms && c->n_grad_calls > 0)
+        FOS_CUDA(cudaMemcpy(r->grad_ms, gm.p, c->n_grad_calls * sizeof(float), cudaMemcpyDeviceToHost));
+    if (r->ls_ms && it > 0) FOS_CUDA(cudaMemcpy(r->ls_ms, lm.p, it * sizeof(float), cudaMemcpyDeviceToHost));
+    r->n_iters = it;
+    r->n_grad_calls = c->n_grad_calls;
+    r->n_passes = c->n_passes;
+    r->stop_reason = c->stop_reason;
+    FOS_CUDA(cudaEventElapsedTime(&r->loop_ms, h->ev0, h->ev1));
+    r->kernel_launches = h->launches - launches0;
+    r->grad_kernel_ms = 0.f;
+    r->grad_kernel_launches = 0;
+    // passes launched after the device reported completion exit immediately: count only the
+    // ones that did work (the first n_passes)
+    for (size_t i = 0; i + 1 < h->prof_used && static_cast<int>(i / 2) < c->n_passes; i += 2) {
+        float ms = 0.f;
+        FOS_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+        r->grad_kernel_ms += ms;
+        r->grad_kernel_launches += 1;
+    }
+    return FOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone prox operators on host buffers
+// ------------------------------------------------------------------------------------------
+static int prox_host(const double* v, int64_t len, double thresh, double scale, double* out, int device) {
+    FOS_REQUIRE(len >= 0 && (len == 0 || (v && out)), "null pointer argument");
+    if (len == 0) return FOS_OK;
+    if (fos_device_count() <= 0) {
+        fos_set_error("no CUDA device visible: libfos_b200 has no CPU fallback");
+        return FOS_ERR_CUDA;
+    }
+    FOS_CUDA(cudaSetDevice(device));
+    double* dv = nullptr;
+    FOS_CUDA(cudaMalloc(&dv, 2 * static_cast<size_t>(len) * sizeof(double)));
+    int st = FOS_OK;
+    cudaError_t e = cudaMemcpy(dv, v, static_cast<size_t>(len) * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        st = fos_launch_prox(dv, dv + len, len, thresh, scale, nullptr);
+        if (st == FOS_OK) e = cudaMemcpy(out, dv + len, static_cast<size_t>(len) * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dv);
+    if (st != FOS_OK) return st;
+    if (e != cudaSuccess) {
+        fos_set_error("prox failed: %s", cudaGetErrorString(e));
+        return FOS_ERR_CUDA;
+    }
+    return FOS_OK;
+}
+
+extern "C" int fos_prox_l1(const double* v, int64_t len, double thresh, double* out, int device) {
+    return prox_host(v, len, thresh, 1.0, out, device);
+}
+
+extern "C" int fos_prox_elastic_net(const double* v, int64_t len, double tau, double alpha1, double alpha2,
+                                    double* out, int device) {
+    return prox_host(v, len, tau * alpha1, 1.0 + tau * alpha2, out, device);
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU plumbing (peer windows are attached by comm.cu; placeholders until then)
+// ------------------------------------------------------------------------------------------
+extern "C" int fos_comm_window_alloc(fos_design*, int, int, void*) {
+    fos_set_error("peer-window exchange not built into this library yet");
+    return FOS_ERR_UNSUPPORTED;
+}
+extern "C" int fos_comm_attach(fos_design*, const void*) {
+    fos_set_error("peer-window exchange not built into this library yet");
+    return FOS_ERR_UNSUPPORTED;
+}
+extern "C" int fos_comm_set_external(fos_design*, int, int) {
+    fos_set_error("external exchange not built into this library yet");
+    return FOS_ERR_UNSUPPORTED;
+}
+extern "C" int fos_comm_partial_dev(fos_design*, double**, int64_t*) {
+    fos_set_error("external exchange not built into this library yet");
+    return FOS_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,226 @@
+// fos_common.cuh -- shared host/device definitions of libfos_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fos.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ------------------------------------------------------------------------------------------
+void fos_set_error(const char* fmt, ...);
+
+#define FOS_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            fos_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                    \
+                          cudaGetErrorString(_e));                                         \
+            return (_e == cudaErrorMemoryAllocation) ? FOS_ERR_NOMEM : FOS_ERR_CUDA;       \
+        }                                                                                  \
+    } while (0)
+
+#define FOS_REQUIRE(cond, ...)                                                             \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            fos_set_error(__VA_ARGS__);                                                    \
+            return FOS_ERR_INVALID;                                                        \
+        }                                                                                  \
+    } while (0)
+
+#define FOS_TRY(expr)                                                                      \
+    do {                                                                                   \
+        int _s = (expr);                                                                   \
+        if (_s != FOS_OK) return _s;                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// pass modes of the gradient kernel (bit set, lives in FosCtrl::g_mode)
+// ------------------------------------------------------------------------------------------
+enum : int {
+    GM_SKIP = 0,
+    GM_GRAD = 1,  // r1 = A v1 - b ; partial_g += A^T r1 ; s1 += r1^2
+    GM_DOT2 = 2,  // r2 = A v2 - b ; s2 += r2^2
+    GM_NOB = 4,   // treat b as zero (power iteration)
+    GM_PROBE = 8, // diagnostic: run the bulk-copy ring only, consumers discard the data
+};
+
+// phases of the proximal-gradient state machine (FosCtrl::phase)
+enum : int {
+    PH_GRAD = 0,      // next pass: gradient at y (+ lagged objective of x_k)
+    PH_TRIAL = 1,     // next pass: smooth value of the Armijo candidate
+    PH_FINALOBJ = 2,  // next pass: objective of the last iterate only
+    PH_DONE = 3,
+};
+
+// epilogue operations
+enum : int {
+    EOP_PG = 0,     // proximal-gradient state machine (fista / fista_delta / ista)
+    EOP_POWER = 1,  // power iteration step
+    EOP_FG = 2,     // g (+a2 x), loss
+    EOP_OBJ = 3,    // objective value
+    EOP_ATB = 4,    // |A^T b|_inf  (lambda_max)
+};
+
+constexpr int FOS_EPI_CLUSTER = 8;    // CTAs in the epilogue cluster (portable maximum)
+constexpr int FOS_EPI_THREADS = 256;  // threads per epilogue CTA
+constexpr int FOS_NSCAL = 8;          // scalars reduced per epilogue
+
+// Control block, one per design, resident in device memory.  The host writes the
+// configuration before a solve; afterwards only the epilogue kernel writes it and the
+// gradient kernel reads g_mode.
+struct FosCtrl {
+    // ---- configuration
+    int scheme, backtracking, adaptive_restart, want_hist, want_obj, max_iter, obj_terms;
+    int pad0;
+    double alpha1, alpha2, eta, tol, tol_ratio, restart_thr, delta, armijo_c;
+    // ---- dynamic state
+    int g_mode, phase, k, shrinks, obj_pending, stop_reason, n_grad_calls, n_passes;
+    double tau, t_mom, prev_step, trial_t, gy, gd, cand_xx, pend_l2, pend_l1;
+    unsigned long long pass_t0;  // %globaltimer at the start of the current pass
+    // ---- power iteration
+    double L, L_prev, ptol;
+    int pit, pit_max;
+    // ---- one-shot outputs
+    double out[4];
+};
+
+// Per-solve device arrays referenced by the epilogue.
+struct FosHist {
+    double* x_hist;     // (max_iter+1) x d   (may be null)
+    double* obj_hist;   // max_iter
+    double* t_hist;     // max_iter+1
+    double* step_hist;  // max_iter
+    int* ls_iters;      // max_iter
+    float* grad_ms;     // max_iter+1
+    float* ls_ms;       // max_iter
+};
+
+// Peer-memory exchange window (multi-GPU).  Every rank owns one window in its own HBM,
+// mapped into all peers through CUDA IPC:  [2 slots][ (ldv + FOS_NSCAL) doubles ] payload,
+// followed by [2 slots][world] 64-bit arrival flags.
+struct FosPeer {
+    int rank, world;
+    double* win[8];                // win[r] = rank r's window as mapped in this process
+    unsigned long long* flag[8];   // flag[r] = rank r's flag array
+    unsigned long long epoch;      // monotonically increasing pass counter (host-managed)
+};
+
+// Everything the gradient kernel needs.
+struct GradArgs {
+    const void* A;
+    const double* b;
+    const double* v1;
+    const double* v2;
+    double* partial_g;   // [n_parts][ldv]
+    double* partial_s;   // [n_parts][2]
+    FosCtrl* ctrl;
+    long long n;
+    int d, lda, ldv;
+    int mode_override;   // >= 0: use instead of ctrl->g_mode
+};
+
+// Everything the epilogue kernel needs.
+struct EpiArgs {
+    FosCtrl* ctrl;
+    FosHist hist;
+    const double* partial_g;
+    const double* partial_s;
+    int n_parts;
+    int d, ldv;
+    int op;
+    int g_mode_ran;      // for one-shot ops: the mode the preceding pass ran with
+    double* y;           // v1 of the next pass
+    double* xc;          // v2 of the next pass (candidate / newest iterate)
+    double* xk;          // current iterate
+    double* g;           // reduced gradient
+    double op_a1, op_a2; // scalars of the one-shot ops
+    int op_bits;
+    // multi-GPU
+    int world, rank;
+    FosPeer peer;
+    unsigned long long epoch;
+};
+
+// ------------------------------------------------------------------------------------------
+// design handle (host side)
+// ------------------------------------------------------------------------------------------
+struct fos_design {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    long long n = 0;
+    int d = 0, lda = 0, ldv = 0;
+    int dtype = FOS_F64;
+    void* A = nullptr;
+    double* b = nullptr;
+    bool owns_A = false, owns_b = false;
+    // workspaces
+    int n_parts = 0;
+    double* partial_g = nullptr;
+    double* partial_s = nullptr;
+    double *y = nullptr, *xc = nullptr, *xk = nullptr, *g = nullptr;
+    FosCtrl* ctrl = nullptr;
+    FosCtrl* ctrl_host = nullptr;  // pinned mirror
+    double* vec_host = nullptr;    // pinned staging, 2*ldv + 8 doubles
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    // multi-GPU
+    int world = 1, rank = 0;
+    int comm_mode = 0;  // 0 none, 1 peer windows, 2 external (host-staged)
+    void* window = nullptr;
+    size_t window_bytes = 0;
+    void* peer_ptr[8] = {nullptr};
+    FosPeer peer{};
+    // gradient kernel selection (chosen at creation)
+    int kern_kind = 0;  // 0 generic, 1 streaming
+    // optional per-launch event timing of the gradient kernel
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+    size_t prof_used = 0;
+};
+
+// launchers implemented in the .cu files
+int fos_launch_grad(fos_design* h, int mode_override);
+int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hist, double a1,
+                        double a2, int bits);
+int fos_grad_plan(fos_design* h);  // picks kernel + n_parts, sets smem attributes
+int fos_launch_prox(const double* v_dev, double* out_dev, long long len, double thresh,
+                    double scale, cudaStream_t stream);
+int fos_launch_synthetic(fos_design* h, unsigned long long seed, double noise, double rho1,
+                         double rho2, long long row0);
+int fos_launch_repack(const void* src_dev, void* dst_dev, long long rows, int d, int lda,
+                      long long row_stride, long long col_stride, int dtype, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned long long fos_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// numpy semantics of sign(v)*maximum(|v|-thr, 0)  (prox_operators.py:8): sign(+-0) = +0,
+// NaN propagates through both factors, a shrunk negative entry becomes -0.0.
+__device__ __forceinline__ double fos_soft_threshold(double v, double thr) {
+    double sgn = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : ((v == 0.0) ? 0.0 : v));
+    double mag = __dsub_rn(fabs(v), thr);
+    double mx = (mag != mag) ? mag : ((mag > 0.0) ? mag : 0.0);
+    return __dmul_rn(sgn, mx);
+}
+
+__device__ __forceinline__ double fos_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__

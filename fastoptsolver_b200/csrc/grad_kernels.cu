@@ -1,0 +1,560 @@
+// grad_kernels.cu -- the fused single-pass gradient  g = A^T (A v1 - b)  (+ second residual
+// norm ||A v2 - b||^2 in the same pass).  Replaces the two dgemv calls of the reference
+// (iterative_solvers.py:173, :292; lbfgs.py:46-48) and the extra dgemv of the objective
+// (iterative_solvers.py:225, objective_functions.py:13): A is streamed from HBM exactly once.
+//
+// Streaming kernel (rows >= 4 KB): one persistent CTA per SM.  A producer thread moves
+// contiguous row groups global -> shared with cp.async.bulk (TMA bulk engine, SASS UBLKCP)
+// into an mbarrier ring with an L2 evict-first policy; NT consumer threads own CPT columns
+// each, keep the row group in registers between the dot product (r_i = a_i . v - b_i) and
+// the rank-1 update (acc += r_i * a_i), and exchange the per-warp dot partials through a
+// double-buffered shared array with ONE named barrier per stage.  Every sum has a fixed
+// order (static row partition, ordered cross-warp and cross-CTA sums), so results are
+// bit-reproducible run to run.
+//
+// HBM bound: algorithmic bytes per pass = n*lda*sizeof(T) + 8n; 4 flop / 8 B in fp64.
+#include "fos_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- PTX wrappers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<double> {
+    static constexpr int N = 2;
+    using type = double2;
+    __device__ static __forceinline__ void load(const void* p, double (&o)[2]) {
+        double2 v = *reinterpret_cast<const double2*>(p);
+        o[0] = v.x;
+        o[1] = v.y;
+    }
+};
+template <>
+struct Vec<float> {
+    static constexpr int N = 4;
+    using type = float4;
+    __device__ static __forceinline__ void load(const void* p, double (&o)[4]) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x;
+        o[1] = v.y;
+        o[2] = v.z;
+        o[3] = v.w;
+    }
+};
+
+constexpr int MAX_STAGES = 8;
+
+// ------------------------------------------------------------------------------------------
+// streaming kernel
+//   NT  consumer threads (plus one producer warp)
+//   CPT columns per consumer thread (NT*CPT >= lda)
+//   R   rows per pipeline stage
+// ------------------------------------------------------------------------------------------
+template <typename T, int NT, int CPT, int R>
+__global__ void __launch_bounds__(NT + 32, 1)
+grad_stream_kernel(GradArgs a, int stage_bytes, int nstage) {
+    constexpr int VEC = Vec<T>::N;
+    constexpr int NV = CPT / VEC;  // vectors per row per thread
+    constexpr int NW = NT / 32;
+    static_assert(CPT % VEC == 0, "CPT must be a multiple of the vector width");
+
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(16) double red[2][NW][R][2];
+
+    const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
+    if ((mode & (GM_GRAD | GM_DOT2 | GM_PROBE)) == 0) return;
+    const bool do_grad = mode & GM_GRAD;
+    const bool do_dot2 = mode & GM_DOT2;
+    const bool use_b = !(mode & GM_NOB);
+    const bool probe = mode & GM_PROBE;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    if (cta == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
+
+    // static contiguous row partition: deterministic summation order
+    const long long lo = (a.n * cta) / ncta;
+    const long long hi = (a.n * (cta + 1LL)) / ncta;
+    const int nst = static_cast<int>((hi - lo + R - 1) / R);
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
+    const unsigned char* Abase = static_cast<const unsigned char*>(a.A);
+
+    if (warp == NW) {
+        // ===== producer warp: one elected lane drives the bulk-copy ring =====
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            for (int s = 0; s < nst; ++s) {
+                const int slot = s % nstage;
+                const int use = s / nstage;
+                if (use > 0) mbar_wait(&empty_bar[slot], (use - 1) & 1);
+                const long long r0 = lo + static_cast<long long>(s) * R;
+                const int rows = static_cast<int>(min(static_cast<long long>(R), hi - r0));
+                const uint32_t bytes = static_cast<uint32_t>(rows * row_bytes);
+                mbar_expect_tx(&full_bar[slot], bytes);
+                bulk_g2s(ring + static_cast<size_t>(slot) * stage_bytes, Abase + r0 * row_bytes,
+                         bytes, &full_bar[slot], pol);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    if (probe) {
+        // streaming ceiling probe: same ring, same bytes, no arithmetic
+        for (int s = 0; s < nst; ++s) {
+            const int slot = s % nstage;
+            mbar_wait(&full_bar[slot], (s / nstage) & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        }
+        return;
+    }
+    double v1[NV][VEC], v2[NV][VEC], acc[NV][VEC];
+    bool colok[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c0 = VEC * (tid + NT * j);
+        colok[j] = c0 < a.lda;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int c = c0 + e;
+            v1[j][e] = (do_grad && c < a.d) ? a.v1[c] : 0.0;
+            v2[j][e] = (do_dot2 && c < a.d) ? a.v2[c] : 0.0;
+            acc[j][e] = 0.0;
+        }
+    }
+    double s1 = 0.0, s2 = 0.0;
+
+    // b values of the next two stages, prefetched by lanes < R of warp 0
+    double b_cur = 0.0, b_nxt = 0.0;
+    auto fetch_b = [&](int s) -> double {
+        if (!use_b || warp != 0 || lane >= R || s >= nst) return 0.0;
+        const long long row = lo + static_cast<long long>(s) * R + lane;
+        return (row < hi) ? __ldg(a.b + row) : 0.0;
+    };
+    b_cur = fetch_b(0);
+    b_nxt = fetch_b(1);
+
+    for (int s = 0; s < nst; ++s) {
+        const int slot = s % nstage;
+        const uint32_t parity = (s / nstage) & 1;
+        const double b_far = fetch_b(s + 2);
+        const long long r0 = lo + static_cast<long long>(s) * R;
+        const int rows = static_cast<int>(min(static_cast<long long>(R), hi - r0));
+        const unsigned char* st = ring + static_cast<size_t>(slot) * stage_bytes;
+
+        mbar_wait(&full_bar[slot], parity);
+
+        double av[R][NV][VEC];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if (r < rows && colok[j]) {
+                    Vec<T>::load(st + r * row_bytes + static_cast<size_t>(VEC) * (tid + NT * j) * sizeof(T),
+                                 av[r][j]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) av[r][j][e] = 0.0;
+                }
+            }
+        }
+
+        // per-thread partial dot products (two chains per row)
+        double d1[R], d2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double p1a = 0.0, p1b = 0.0, p2a = 0.0, p2b = 0.0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if (((j * VEC + e) & 1) == 0) {
+                        if (do_grad) p1a = fma(av[r][j][e], v1[j][e], p1a);
+                        if (do_dot2) p2a = fma(av[r][j][e], v2[j][e], p2a);
+                    } else {
+                        if (do_grad) p1b = fma(av[r][j][e], v1[j][e], p1b);
+                        if (do_dot2) p2b = fma(av[r][j][e], v2[j][e], p2b);
+                    }
+                }
+            }
+            d1[r] = p1a + p1b;
+            d2[r] = p2a + p2b;
+        }
+        // the stage's bytes now live in registers: hand the slot back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (do_grad) d1[r] = fos_warp_sum(d1[r]);
+            if (do_dot2) d2[r] = fos_warp_sum(d2[r]);
+        }
+        const int par = s & 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (lane == r) {
+                // warp 0 folds -b_i into its partial so that the ordered sum below yields r_i
+                const double bi = (warp == 0) ? b_cur : 0.0;
+                red[par][warp][r][0] = d1[r] - (do_grad ? bi : 0.0);
+                red[par][warp][r][1] = d2[r] - (do_dot2 ? bi : 0.0);
+            }
+        }
+        named_bar_sync(1, NT);
+
+        double r1[R], r2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double2 pr = *reinterpret_cast<const double2*>(&red[par][w][r][0]);
+                t1 += pr.x;
+                t2 += pr.y;
+            }
+            r1[r] = t1;
+            r2[r] = t2;
+        }
+        if (do_grad) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[j][e] = fma(r1[r], av[r][j][e], acc[j][e]);
+                }
+            }
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < rows) {
+                    s1 = fma(r1[r], r1[r], s1);
+                    s2 = fma(r2[r], r2[r], s2);
+                }
+            }
+        }
+        b_cur = b_nxt;
+        b_nxt = b_far;
+    }
+
+    if (do_grad) {
+        double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c0 = VEC * (tid + NT * j);
+            if (c0 < a.ldv) {
+#pragma unroll
+                for (int e = 0; e < VEC; e += 2) {
+                    if (c0 + e < a.ldv)
+                        *reinterpret_cast<double2*>(out + c0 + e) = make_double2(acc[j][e], acc[j][e + 1]);
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        a.partial_s[2 * cta + 0] = s1;
+        a.partial_s[2 * cta + 1] = s2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic kernel (lda <= 512): one warp per contiguous row block, lane owns columns
+// lane + 32 j.  Direct coalesced global loads, two rows in flight per warp.
+// ------------------------------------------------------------------------------------------
+constexpr int GEN_WARPS = 8;
+
+template <typename T, int J>
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+grad_generic_kernel(GradArgs a) {
+    __shared__ double wacc[GEN_WARPS][J * 32];
+    __shared__ double wsc[GEN_WARPS][2];
+
+    const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
+    if ((mode & (GM_GRAD | GM_DOT2)) == 0) return;
+    const bool do_grad = mode & GM_GRAD;
+    const bool do_dot2 = mode & GM_DOT2;
+    const bool use_b = !(mode & GM_NOB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (blockIdx.x == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
+    const long long W = static_cast<long long>(gridDim.x) * GEN_WARPS;
+    const long long gw = static_cast<long long>(blockIdx.x) * GEN_WARPS + warp;
+    const long long lo = (a.n * gw) / W, hi = (a.n * (gw + 1)) / W;
+
+    double v1[J], v2[J], acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int c = lane + 32 * j;
+        v1[j] = (do_grad && c < a.d) ? a.v1[c] : 0.0;
+        v2[j] = (do_dot2 && c < a.d) ? a.v2[c] : 0.0;
+        acc[j] = 0.0;
+    }
+    double s1 = 0.0, s2 = 0.0;
+    const T* A = static_cast<const T*>(a.A);
+
+    long long row = lo;
+    for (; row + 1 < hi; row += 2) {
+        double a0[J], a1[J];
+        const T* p0 = A + row * a.lda;
+        const T* p1 = p0 + a.lda;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int c = lane + 32 * j;
+            a0[j] = (c < a.lda) ? static_cast<double>(__ldg(p0 + c)) : 0.0;
+            a1[j] = (c < a.lda) ? static_cast<double>(__ldg(p1 + c)) : 0.0;
+        }
+        const double b0 = use_b ? __ldg(a.b + row) : 0.0;
+        const double b1 = use_b ? __ldg(a.b + row + 1) : 0.0;
+        double d10 = 0.0, d11 = 0.0, d20 = 0.0, d21 = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (do_grad) {
+                d10 = fma(a0[j], v1[j], d10);
+                d11 = fma(a1[j], v1[j], d11);
+            }
+            if (do_dot2) {
+                d20 = fma(a0[j], v2[j], d20);
+                d21 = fma(a1[j], v2[j], d21);
+            }
+        }
+        if (do_grad) {
+            d10 = fos_warp_sum(d10) - b0;
+            d11 = fos_warp_sum(d11) - b1;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = fma(d11, a1[j], fma(d10, a0[j], acc[j]));
+            s1 = fma(d11, d11, fma(d10, d10, s1));
+        }
+        if (do_dot2) {
+            d20 = fos_warp_sum(d20) - b0;
+            d21 = fos_warp_sum(d21) - b1;
+            s2 = fma(d21, d21, fma(d20, d20, s2));
+        }
+    }
+    if (row < hi) {
+        double a0[J];
+        const T* p0 = A + row * a.lda;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int c = lane + 32 * j;
+            a0[j] = (c < a.lda) ? static_cast<double>(__ldg(p0 + c)) : 0.0;
+        }
+        const double b0 = use_b ? __ldg(a.b + row) : 0.0;
+        double d10 = 0.0, d20 = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (do_grad) d10 = fma(a0[j], v1[j], d10);
+            if (do_dot2) d20 = fma(a0[j], v2[j], d20);
+        }
+        if (do_grad) {
+            d10 = fos_warp_sum(d10) - b0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = fma(d10, a0[j], acc[j]);
+            s1 = fma(d10, d10, s1);
+        }
+        if (do_dot2) {
+            d20 = fos_warp_sum(d20) - b0;
+            s2 = fma(d20, d20, s2);
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < J; ++j) wacc[warp][lane + 32 * j] = acc[j];
+    if (lane == 0) {
+        wsc[warp][0] = s1;
+        wsc[warp][1] = s2;
+    }
+    __syncthreads();
+    if (do_grad) {
+        for (int c = tid; c < a.ldv && c < J * 32; c += GEN_WARPS * 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < GEN_WARPS; ++w) t += wacc[w][c];
+            a.partial_g[static_cast<size_t>(blockIdx.x) * a.ldv + c] = t;
+        }
+    }
+    if (tid == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < GEN_WARPS; ++w) {
+            t1 += wsc[w][0];
+            t2 += wsc[w][1];
+        }
+        a.partial_s[2 * blockIdx.x + 0] = t1;
+        a.partial_s[2 * blockIdx.x + 1] = t2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------
+struct StreamCfg {
+    const void* fn;
+    int nt, cpt, r;
+};
+
+template <typename T, int NT, int CPT, int R>
+StreamCfg make_cfg() {
+    return StreamCfg{reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R>), NT, CPT, R};
+}
+
+bool pick_stream_cfg(int dtype, int lda, StreamCfg* out) {
+    if (dtype == FOS_F64) {
+        if (lda <= 512) *out = make_cfg<double, 256, 2, 8>();
+        else if (lda <= 1024) *out = make_cfg<double, 256, 4, 4>();
+        else if (lda <= 2048) *out = make_cfg<double, 256, 8, 2>();
+        else if (lda <= 4096) *out = make_cfg<double, 256, 16, 1>();
+        else if (lda <= 8192) *out = make_cfg<double, 512, 16, 1>();
+        else return false;
+    } else {
+        if (lda <= 1024) *out = make_cfg<float, 256, 4, 8>();
+        else if (lda <= 2048) *out = make_cfg<float, 256, 8, 4>();
+        else if (lda <= 4096) *out = make_cfg<float, 256, 16, 2>();
+        else if (lda <= 8192) *out = make_cfg<float, 512, 16, 1>();
+        else return false;
+    }
+    return true;
+}
+
+template <typename T>
+const void* pick_generic(int lda) {
+    if (lda <= 32) return reinterpret_cast<const void*>(&grad_generic_kernel<T, 1>);
+    if (lda <= 64) return reinterpret_cast<const void*>(&grad_generic_kernel<T, 2>);
+    if (lda <= 128) return reinterpret_cast<const void*>(&grad_generic_kernel<T, 4>);
+    if (lda <= 256) return reinterpret_cast<const void*>(&grad_generic_kernel<T, 8>);
+    return reinterpret_cast<const void*>(&grad_generic_kernel<T, 16>);
+}
+
+constexpr int SMEM_RING_BUDGET = 200 * 1024;
+
+}  // namespace
+
+// Chooses the kernel and the number of partial rows.  Called once per design, before the
+// workspaces are allocated (n_parts sizes them).
+int fos_grad_plan(fos_design* h) {
+    const char* force = getenv("FOS_FORCE_KERNEL");  // "generic" | "stream" (tests)
+    bool want_stream = h->lda > 512;
+    if (force && std::string(force) == "generic" && h->lda <= 512) want_stream = false;
+    if (force && std::string(force) == "stream" && h->lda * (h->dtype == FOS_F64 ? 8 : 4) >= 16)
+        want_stream = true;
+    StreamCfg cfg;
+    if (want_stream) {
+        if (!pick_stream_cfg(h->dtype, h->lda, &cfg)) {
+            fos_set_error("d = %d exceeds the streaming kernel's limit of 8192 columns", h->d);
+            return FOS_ERR_UNSUPPORTED;
+        }
+        h->kern_kind = 1;
+        long long per = (h->n + h->sm_count - 1) / h->sm_count;
+        h->n_parts = (per >= 1) ? h->sm_count : 1;
+        if (h->n < h->sm_count) h->n_parts = static_cast<int>(h->n > 0 ? h->n : 1);
+        FOS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SMEM_RING_BUDGET));
+    } else {
+        h->kern_kind = 0;
+        long long want = (h->n + GEN_WARPS * 16 - 1) / (GEN_WARPS * 16);
+        long long cap = static_cast<long long>(h->sm_count) * 4;
+        h->n_parts = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+    }
+    return FOS_OK;
+}
+
+int fos_launch_grad(fos_design* h, int mode_override) {
+    GradArgs a;
+    a.A = h->A;
+    a.b = h->b;
+    a.v1 = h->y;
+    a.v2 = h->xc;
+    a.partial_g = h->partial_g;
+    a.partial_s = h->partial_s;
+    a.ctrl = h->ctrl;
+    a.n = h->n;
+    a.d = h->d;
+    a.lda = h->lda;
+    a.ldv = h->ldv;
+    a.mode_override = mode_override;
+    void* params[3];
+    params[0] = &a;
+    if (h->kern_kind == 1) {
+        StreamCfg cfg;
+        pick_stream_cfg(h->dtype, h->lda, &cfg);
+        const int elem = (h->dtype == FOS_F64) ? 8 : 4;
+        int stage_bytes = cfg.r * h->lda * elem;
+        stage_bytes = (stage_bytes + 127) & ~127;
+        int nstage = SMEM_RING_BUDGET / stage_bytes;
+        if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+        if (nstage < 2) {
+            fos_set_error("row too large for the shared-memory ring (stage %d bytes)", stage_bytes);
+            return FOS_ERR_UNSUPPORTED;
+        }
+        params[1] = &stage_bytes;
+        params[2] = &nstage;
+        FOS_CUDA(cudaLaunchKernel(cfg.fn, dim3(h->n_parts), dim3(cfg.nt + 32), params,
+                                  static_cast<size_t>(nstage) * stage_bytes, h->stream));
+    } else {
+        const void* fn = (h->dtype == FOS_F64) ? pick_generic<double>(h->lda) : pick_generic<float>(h->lda);
+        FOS_CUDA(cudaLaunchKernel(fn, dim3(h->n_parts), dim3(GEN_WARPS * 32), params, 0, h->stream));
+    }
+    h->launches++;
+    return FOS_OK;
+}

@@ -1,0 +1,187 @@
+/*
+ * fos.h -- C ABI of libfos_b200.so, the B200 (sm_100a) solver core behind
+ * FastOptSolver's Python module API.
+ *
+ * The reference (ElBaldo1/FastOptSolver) has no FFI layer: its boundary is the
+ * flat Python modules iterative_solvers.py / prox_operators.py /
+ * objective_functions.py / lbfgs.py.  Each entry point below names the reference
+ * interface it replaces (file:line into the reference tree).  The Python drop-in
+ * (the modules under fastoptsolver_b200/dropin) binds these with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns FOS_OK (0) or a negative fos_status; the message of
+ *     the last failure on the calling thread is fos_last_error();
+ *   - all pointers are HOST pointers unless the name ends in _dev;
+ *   - vectors are float64; the design matrix A is float64 or float32 *storage*
+ *     (arithmetic is always float64, as in the reference where numpy up-casts:
+ *     iterative_solvers.py:150);
+ *   - a design handle is NOT re-entrant (the reference keeps module-global metric
+ *     lists and is single-threaded too: iterative_solvers.py:16-18).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with FOS_ERR_CUDA.
+ */
+#ifndef FOS_B200_H
+#define FOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOS_ABI_VERSION 1
+
+typedef enum fos_status {
+    FOS_OK = 0,
+    FOS_ERR_INVALID = -1,  /* bad argument -> ValueError in the drop-in */
+    FOS_ERR_CUDA = -2,     /* CUDA runtime / launch failure -> RuntimeError */
+    FOS_ERR_NOMEM = -3,    /* device or pinned allocation failed */
+    FOS_ERR_UNSUPPORTED = -4,
+    FOS_ERR_COMM = -5      /* multi-GPU exchange failed */
+} fos_status;
+
+typedef enum fos_dtype { FOS_F64 = 0, FOS_F32 = 1 } fos_dtype;
+
+/* momentum scheme of the proximal-gradient engine */
+typedef enum fos_scheme {
+    FOS_SCHEME_NESTEROV = 0, /* fista        iterative_solvers.py:132-245 */
+    FOS_SCHEME_DELTA = 1,    /* fista_delta  iterative_solvers.py:251-344 */
+    FOS_SCHEME_ISTA = 2      /* ista         iterative_solvers.py:65-125 (framework-owned callables) */
+} fos_scheme;
+
+typedef enum fos_stop {
+    FOS_STOP_MAXITER = 0,
+    FOS_STOP_GRADNORM = 1, /* iterative_solvers.py:179 */
+    FOS_STOP_STEP = 2,     /* iterative_solvers.py:238, :337, :122 */
+    FOS_STOP_RATIO = 3     /* iterative_solvers.py:242, :341 */
+} fos_stop;
+
+typedef struct fos_design fos_design; /* opaque: A and b resident in HBM + workspaces */
+
+/* ---- library / device -------------------------------------------------------------- */
+int fos_abi_version(void);
+const char* fos_last_error(void);
+/* number of visible CUDA devices (0 on a CPU box; never fails) */
+int fos_device_count(void);
+/* sm_count, total/free HBM bytes of `device` */
+int fos_device_info(int device, int* sm_count, size_t* total_bytes, size_t* free_bytes);
+
+/* ---- design: A (n x d) and b (n) resident on one GPU ---------------------------------
+ * Replaces the numpy arrays every reference solver takes as (A, b)
+ * (iterative_solvers.py:133-134, lbfgs.py:41, objective_functions.py:3).
+ * The matrix is copied into a row-major device layout whose leading dimension is
+ * padded to 16 bytes; row_stride/col_stride are the host strides in ELEMENTS, so
+ * C-order is (d, 1) and Fortran order is (1, n).  The host arrays are never written. */
+int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
+                      int64_t row_stride, int64_t col_stride, int device, fos_design** out);
+/* Borrow a row-major matrix already resident on `device` (lda in elements, lda*elem
+ * multiple of 16 bytes, base 16-byte aligned); b_dev is float64.  Not freed by destroy. */
+int fos_design_create_device(const void* A_dev, const double* b_dev, int64_t n, int64_t d,
+                             int dtype, int64_t lda, int device, fos_design** out);
+/* Generate the correlated-column synthetic design directly in HBM with a counter-based
+ * (Philox4x32-10) generator: population-standardised version of the recipe in
+ * easy_boston_data.py:23-43 generalised to d columns; rows [row0, row0+n) of a virtual
+ * n_total-row design, so that R ranks generate disjoint shards of the same matrix. */
+int fos_design_create_synthetic(int64_t n, int64_t d, int dtype, uint64_t seed, double noise_std,
+                                double rho1, double rho2, int64_t row0, int device,
+                                fos_design** out);
+int fos_design_destroy(fos_design* h);
+int fos_design_shape(const fos_design* h, int64_t* n, int64_t* d, int* dtype, int64_t* lda);
+/* copy rows [row0, row0+rows) back to the host as a dense C-order block (for the CPU
+ * baseline, which must see the same numbers) */
+int fos_design_download(fos_design* h, int64_t row0, int64_t rows, void* A_out, double* b_out);
+/* device pointers of the resident arrays (for zero-copy wrappers) */
+int fos_design_pointers(fos_design* h, void** A_dev, double** b_dev);
+/* enable/disable per-launch CUDA-event timing of the gradient kernel inside the solver loop */
+int fos_design_set_profile(fos_design* h, int enable);
+/* Diagnostic: average duration (CUDA events, solver stream) of `reps` back-to-back launches of
+ * the gradient kernel in a given mode: 1 = gradient, 3 = gradient + second residual norm,
+ * 2 = residual norm only, 8 = streaming probe (bulk-copy ring only, no arithmetic: the sustained
+ * HBM read ceiling of this pipeline). */
+int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms_avg);
+/* lambda_max = ||A^T b||_inf (one fused pass), the usual scale for alpha1 */
+int fos_design_lambda_max(fos_design* h, double* out);
+
+/* ---- multi-GPU: rows of A sharded over `world` processes, one per GPU -----------------
+ * The exchange step is one all-reduce of the d-length A^T r partial (+2 scalars) per pass.
+ * Peer-memory mode: every rank allocates an exchange window with fos_comm_window_alloc,
+ * publishes its cudaIpcMemHandle (64 bytes) out of band (the drop-in uses
+ * torch.distributed.all_gather), and maps the peers' windows with fos_comm_attach; the
+ * epilogue kernel then reduces across NVLink in fixed rank order inside the same launch. */
+int fos_comm_window_alloc(fos_design* h, int rank, int world, void* ipc_handle_out64);
+int fos_comm_attach(fos_design* h, const void* ipc_handles /* world x 64 bytes */);
+/* Host-staged mode (any backend, used by the gloo tests and as NCCL fallback): the pass is
+ * split so that the caller can all-reduce the (d+2) partial itself between the halves. */
+int fos_comm_set_external(fos_design* h, int rank, int world);
+int fos_comm_partial_dev(fos_design* h, double** partial_dev, int64_t* count);
+
+/* ---- one-shot operators ----------------------------------------------------------------
+ * fos_grad: loss = 0.5||Ax-b||^2 (+0.5 a2 ||x||^2), g = A^T(Ax-b) (+a2 x), A read ONCE.
+ *   replaces the inlined gradient iterative_solvers.py:173-175, :292-294 and `fg`
+ *   lbfgs.py:46-51. */
+int fos_grad(fos_design* h, const double* x, double alpha2, double* g_out, double* loss_out);
+/* fos_objective: objective_functions.py:3-30.  reg: bit0 = add alpha1*||x||_1,
+ * bit1 = add 0.5*alpha2*||x||^2 (lasso=1, ridge=2, elasticnet=3). */
+int fos_objective(fos_design* h, const double* x, int reg_bits, double alpha1, double alpha2,
+                  double* out);
+/* fos_power_iter: estimate_lipschitz, iterative_solvers.py:45-60.  v0 is the caller's
+ * normalised start vector (the drop-in draws it from numpy's legacy global RNG so the
+ * stream advances exactly as in the reference, :50). */
+int fos_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out,
+                   int* iters_out, float* gpu_ms_out);
+/* prox_operators.py:3-8 and :10-16 on a flat host buffer (any shape flattened).
+ * scale = 1/(1+tau*alpha2) for the elastic-net prox, 1.0 for prox_l1. */
+int fos_prox_l1(const double* v, int64_t len, double thresh, double* out, int device);
+int fos_prox_elastic_net(const double* v, int64_t len, double tau, double alpha1, double alpha2,
+                         double* out, int device);
+
+/* ---- the proximal-gradient engine: fista / fista_delta / ista ---------------------------- */
+typedef struct fos_pg_params {
+    int scheme;            /* fos_scheme */
+    double alpha1, alpha2; /* L1 weight (prox), L2 weight (smooth part) */
+    int obj_terms;         /* bits as fos_objective.reg_bits: terms in the recorded objective
+                              (fista: from alpha>0, :227-230; fista_delta: from reg_type, :321) */
+    double delta;          /* FISTA-delta momentum parameter (> 2) */
+    int backtracking;      /* Armijo rule of the reference, :183-197 */
+    double eta;
+    double armijo_c;       /* module global C, iterative_solvers.py:11 */
+    double step0;          /* initial step t_init_factor / L */
+    int max_iter;
+    double tol, tol_ratio;
+    int adaptive_restart;
+    double restart_threshold;
+    int want_history;      /* record iterates (and objectives unless scheme == ISTA) */
+    const double* x0;      /* start point (ISTA only; NULL = zeros) */
+} fos_pg_params;
+
+typedef struct fos_pg_result {
+    /* caller-allocated outputs (NULL = not wanted) */
+    double* x;        /* d                     final iterate */
+    double* x_hist;   /* (max_iter+1) x d      row 0 = x0, row k = x_k   (want_history) */
+    double* obj_hist; /* max_iter              objective of x_1..         (want_history) */
+    double* t_hist;   /* max_iter+1            step size after each iteration (t_hist[0]=step0) */
+    double* step_hist;/* max_iter              ||x_{k+1}-x_k|| */
+    int* ls_iters;    /* max_iter              Armijo shrink count per iteration */
+    float* grad_ms;   /* max_iter+1            device time of each gradient pass */
+    float* ls_ms;     /* max_iter              device time of each line search */
+    /* scalars written by the call */
+    int n_iters;      /* completed iterations */
+    int n_grad_calls; /* gradient passes (== iterations, +1 when the gradient-norm stop fired) */
+    int n_passes;     /* passes over A, everything included */
+    int stop_reason;  /* fos_stop */
+    float loop_ms;    /* device time of the whole loop (CUDA events on the solver stream) */
+    int64_t kernel_launches;
+    /* filled when fos_design_set_profile(h, 1): CUDA events around every gradient-kernel
+     * launch of the loop (on the solver stream), summed */
+    float grad_kernel_ms;
+    int grad_kernel_launches;
+} fos_pg_result;
+
+int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOS_B200_H */

