@@ -3,14 +3,17 @@
 // (iterative_solvers.py:173, :292; lbfgs.py:46-48) and the extra dgemv of the objective
 // (iterative_solvers.py:225, objective_functions.py:13): A is streamed from HBM exactly once.
 //
-// Streaming kernel (rows >= 4 KB): one persistent CTA per SM.  A producer thread moves
-// contiguous row groups global -> shared with cp.async.bulk (TMA bulk engine, SASS UBLKCP)
-// into an mbarrier ring with an L2 evict-first policy; NT consumer threads own CPT columns
-// each, keep the row group in registers between the dot product (r_i = a_i . v - b_i) and
-// the rank-1 update (acc += r_i * a_i), and exchange the per-warp dot partials through a
-// double-buffered shared array with ONE named barrier per stage.  Every sum has a fixed
-// order (static row partition, ordered cross-warp and cross-CTA sums), so results are
-// bit-reproducible run to run.
+// Streaming kernel (d > 512): one persistent CTA per SM.  A producer thread moves contiguous
+// row groups global -> shared with cp.async.bulk (TMA bulk engine, SASS UBLKCP) into an
+// mbarrier ring with an L2 evict-first policy; NT consumer threads own CPT columns each, keep
+// the row group in registers between the dot product (r_i = a_i . v - b_i) and the rank-1
+// update (acc += r_i * a_i), and exchange the per-warp dot partials through a double-buffered
+// shared array with ONE named barrier per stage.  Every sum has a fixed order (static row
+// partition, ordered cross-warp and cross-CTA sums), so results are bit-reproducible.
+//
+// The pass mode (gradient / second dot / both) is read from the device control block and
+// dispatched ONCE per CTA to a compile-time specialised loop, so the steady-state loop has
+// no mode predicates, no column guards and no integer division.
 //
 // HBM bound: algorithmic bytes per pass = n*lda*sizeof(T) + 8n; 4 flop / 8 B in fp64.
 #include "fos_common.cuh"
@@ -72,24 +75,24 @@ template <>
 struct Vec<double> {
     static constexpr int N = 2;
     using type = double2;
-    __device__ static __forceinline__ void load(const void* p, double (&o)[2]) {
-        double2 v = *reinterpret_cast<const double2*>(p);
-        o[0] = v.x;
-        o[1] = v.y;
+    __device__ static __forceinline__ void load_shared(uint32_t addr, double (&o)[2]) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
     }
 };
 template <>
 struct Vec<float> {
     static constexpr int N = 4;
     using type = float4;
-    __device__ static __forceinline__ void load(const void* p, double (&o)[4]) {
-        float4 v = *reinterpret_cast<const float4*>(p);
-        o[0] = v.x;
-        o[1] = v.y;
-        o[2] = v.z;
-        o[3] = v.w;
+    __device__ static __forceinline__ void load_shared(uint32_t addr, double (&o)[4]) {
+        float x, y, z, w;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(addr));
+        o[0] = x;
+        o[1] = y;
+        o[2] = z;
+        o[3] = w;
     }
 };
+
 
 constexpr int MAX_STAGES = 8;
 
@@ -99,28 +102,199 @@ constexpr int MAX_STAGES = 8;
 //   CPT columns per consumer thread (NT*CPT >= lda)
 //   R   rows per pipeline stage
 // ------------------------------------------------------------------------------------------
-template <typename T, int NT, int CPT, int R>
-__global__ void __launch_bounds__(NT + 32, 1)
-grad_stream_kernel(GradArgs a, int stage_bytes, int nstage) {
-    constexpr int VEC = Vec<T>::N;
-    constexpr int NV = CPT / VEC;  // vectors per row per thread
-    constexpr int NW = NT / 32;
-    static_assert(CPT % VEC == 0, "CPT must be a multiple of the vector width");
+template <int NW, int R>
+struct StreamSmem {
+    uint64_t full_bar[MAX_STAGES];
+    double red[2][R][NW][2];  // [parity][row][warp][dot1, dot2]
+};
 
+// Consumer loop, specialised on the pass mode.  GRAD: first dot + rank-1 update;
+// DOT2: second dot.  Column guards are folded into per-thread shared-memory offsets
+// (an out-of-range column reads offset 0 and multiplies it by a zero vector entry).
+template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2>
+__device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
+                                               unsigned char* ring, int stage_bytes, int nstage,
+                                               long long lo, long long hi, bool use_b, uint64_t pol) {
+    constexpr int VEC = Vec<T>::N;
+    constexpr int NV = CPT / VEC;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x;
+    const uint32_t row_bytes = static_cast<uint32_t>(a.lda) * sizeof(T);
+    const int nst = static_cast<int>((hi - lo + R - 1) / R);
+
+    double v1[NV][VEC], v2[NV][VEC], acc[NV][VEC];
+    uint32_t off[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c0 = VEC * (tid + NT * j);
+        off[j] = (c0 < a.lda) ? static_cast<uint32_t>(c0) * sizeof(T) : 0u;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int c = c0 + e;
+            v1[j][e] = (GRAD && c < a.d) ? a.v1[c] : 0.0;
+            v2[j][e] = (DOT2 && c < a.d) ? a.v2[c] : 0.0;
+            acc[j][e] = 0.0;
+        }
+    }
+    double s1 = 0.0, s2 = 0.0;
+
+    // b values of the next two stages, prefetched by lanes < R of warp 0
+    const bool b_lane = use_b && warp == 0 && lane < R;
+    const double* bp = a.b + lo + lane;
+    long long b_left = hi - lo - lane;  // rows remaining for this lane's prefetch stream
+    double b_cur = 0.0, b_nxt = 0.0;
+    if (b_lane && b_left > 0) b_cur = __ldg(bp);
+    if (b_lane && b_left > R) b_nxt = __ldg(bp + R);
+
+    const uint32_t ring_u32 = smem_u32(ring);
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int s = 0; s < nst; ++s) {
+        double b_far = 0.0;
+        if (b_lane && b_left > 2 * R) b_far = __ldg(bp + 2 * R);
+        bp += R;
+        b_left -= R;
+        const int rows = static_cast<int>(min(static_cast<long long>(R), hi - lo - static_cast<long long>(s) * R));
+        const uint32_t st = ring_u32 + static_cast<uint32_t>(slot) * static_cast<uint32_t>(stage_bytes);
+
+        mbar_wait(&sm.full_bar[slot], parity);
+
+        double av[R][NV][VEC];
+        if (rows == R) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) Vec<T>::load_shared(st + r * row_bytes + off[j], av[r][j]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    if (r < rows) {
+                        Vec<T>::load_shared(st + r * row_bytes + off[j], av[r][j]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) av[r][j][e] = 0.0;
+                    }
+                }
+        }
+
+        // per-thread partial dots: two independent chains per dot
+        double d1[R], d2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double p1a = 0.0, p1b = 0.0, p2a = 0.0, p2b = 0.0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if (((j * VEC + e) & 1) == 0) {
+                        if (GRAD) p1a = fma(av[r][j][e], v1[j][e], p1a);
+                        if (DOT2) p2a = fma(av[r][j][e], v2[j][e], p2a);
+                    } else {
+                        if (GRAD) p1b = fma(av[r][j][e], v1[j][e], p1b);
+                        if (DOT2) p2b = fma(av[r][j][e], v2[j][e], p2b);
+                    }
+                }
+            d1[r] = GRAD ? p1a + p1b : 0.0;
+            d2[r] = DOT2 ? p2a + p2b : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (GRAD) d1[r] = fos_warp_sum(d1[r]);
+            if (DOT2) d2[r] = fos_warp_sum(d2[r]);
+        }
+        const int par = s & 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (lane == r) {
+                // warp 0 folds -b_i into its partial so that the ordered sum below yields r_i
+                const double bi = (warp == 0) ? b_cur : 0.0;
+                *reinterpret_cast<double2*>(&sm.red[par][r][warp][0]) =
+                    make_double2(GRAD ? d1[r] - bi : 0.0, DOT2 ? d2[r] - bi : 0.0);
+            }
+        }
+        __syncthreads();
+        // Every consumer has copied stage s into registers before arriving at the barrier, so
+        // its slot is free: thread 0 refills it with stage s + nstage (no empty barriers needed).
+        if (tid == 0 && s + nstage < nst) {
+            const long long rs = lo + static_cast<long long>(s + nstage) * R;
+            const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
+            const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
+            mbar_expect_tx(&sm.full_bar[slot], bytes);
+            bulk_g2s(ring + static_cast<size_t>(slot) * stage_bytes,
+                     static_cast<const unsigned char*>(a.A) + static_cast<size_t>(rs) * row_bytes, bytes,
+                     &sm.full_bar[slot], pol);
+        }
+
+        // ordered (pairwise tree) sum over the NW warp partials; all loads issue first
+        double r1[R], r2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double2 pr[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) pr[w] = *reinterpret_cast<const double2*>(&sm.red[par][r][w][0]);
+#pragma unroll
+            for (int span = 1; span < NW; span *= 2)
+#pragma unroll
+                for (int w = 0; w + span < NW; w += 2 * span) {
+                    if (GRAD) pr[w].x += pr[w + span].x;
+                    if (DOT2) pr[w].y += pr[w + span].y;
+                }
+            r1[r] = pr[0].x;
+            r2[r] = pr[0].y;
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[j][e] = fma(r1[r], av[r][j][e], acc[j][e]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < rows) {
+                if (GRAD) s1 = fma(r1[r], r1[r], s1);
+                if (DOT2) s2 = fma(r2[r], r2[r], s2);
+            }
+        }
+        b_cur = b_nxt;
+        b_nxt = b_far;
+        if (++slot == nstage) {
+            slot = 0;
+            parity ^= 1u;
+        }
+    }
+
+    if (GRAD) {
+        double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c0 = VEC * (tid + NT * j);
+#pragma unroll
+            for (int e = 0; e < VEC; e += 2)
+                if (c0 + e < a.ldv) *reinterpret_cast<double2*>(out + c0 + e) = make_double2(acc[j][e], acc[j][e + 1]);
+        }
+    }
+    if (tid == 0) {
+        a.partial_s[2 * cta + 0] = s1;
+        a.partial_s[2 * cta + 1] = s2;
+    }
+}
+
+template <typename T, int NT, int CPT, int R>
+__global__ void __launch_bounds__(NT, 1)
+grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char ring[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(16) double red[2][NW][R][2];
+    __shared__ __align__(16) StreamSmem<NW, R> sm;
 
     const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
     if ((mode & (GM_GRAD | GM_DOT2 | GM_PROBE)) == 0) return;
-    const bool do_grad = mode & GM_GRAD;
-    const bool do_dot2 = mode & GM_DOT2;
-    const bool use_b = !(mode & GM_NOB);
-    const bool probe = mode & GM_PROBE;
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (cta == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
 
@@ -129,194 +303,61 @@ grad_stream_kernel(GradArgs a, int stage_bytes, int nstage) {
     const long long hi = (a.n * (cta + 1LL)) / ncta;
     const int nst = static_cast<int>((hi - lo + R - 1) / R);
 
+    uint64_t pol = 0;
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], NW);
-        }
+        for (int s = 0; s < nstage; ++s) mbar_init(&sm.full_bar[s], 1);
         mbar_fence_init();
+        // prologue: fill the ring (thread 0 is also the only thread that refills it later)
+        pol = l2_evict_first_policy();
+        const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
+        for (int s = 0; s < nstage && s < nst; ++s) {
+            const long long rs = lo + static_cast<long long>(s) * R;
+            const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
+            const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
+            mbar_expect_tx(&sm.full_bar[s], bytes);
+            bulk_g2s(ring + static_cast<size_t>(s) * stage_bytes,
+                     static_cast<const unsigned char*>(a.A) + static_cast<size_t>(rs) * row_bytes, bytes,
+                     &sm.full_bar[s], pol);
+        }
     }
     __syncthreads();
 
-    const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
-    const unsigned char* Abase = static_cast<const unsigned char*>(a.A);
-
-    if (warp == NW) {
-        // ===== producer warp: one elected lane drives the bulk-copy ring =====
-        if (lane == 0) {
-            const uint64_t pol = l2_evict_first_policy();
-            for (int s = 0; s < nst; ++s) {
-                const int slot = s % nstage;
-                const int use = s / nstage;
-                if (use > 0) mbar_wait(&empty_bar[slot], (use - 1) & 1);
-                const long long r0 = lo + static_cast<long long>(s) * R;
-                const int rows = static_cast<int>(min(static_cast<long long>(R), hi - r0));
-                const uint32_t bytes = static_cast<uint32_t>(rows * row_bytes);
-                mbar_expect_tx(&full_bar[slot], bytes);
-                bulk_g2s(ring + static_cast<size_t>(slot) * stage_bytes, Abase + r0 * row_bytes,
-                         bytes, &full_bar[slot], pol);
-            }
-        }
-        return;
-    }
-
     // ===== consumers =====
-    if (probe) {
+    if (mode & GM_PROBE) {
         // streaming ceiling probe: same ring, same bytes, no arithmetic
+        int slot = 0;
+        uint32_t parity = 0;
         for (int s = 0; s < nst; ++s) {
-            const int slot = s % nstage;
-            mbar_wait(&full_bar[slot], (s / nstage) & 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+            mbar_wait(&sm.full_bar[slot], parity);
+            __syncthreads();
+            if (tid == 0 && s + nstage < nst) {
+                const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
+                const long long rs = lo + static_cast<long long>(s + nstage) * R;
+                const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
+                const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
+                mbar_expect_tx(&sm.full_bar[slot], bytes);
+                bulk_g2s(ring + static_cast<size_t>(slot) * stage_bytes,
+                         static_cast<const unsigned char*>(a.A) + static_cast<size_t>(rs) * row_bytes, bytes,
+                         &sm.full_bar[slot], pol);
+            }
+            if (++slot == nstage) {
+                slot = 0;
+                parity ^= 1u;
+            }
         }
         return;
     }
-    double v1[NV][VEC], v2[NV][VEC], acc[NV][VEC];
-    bool colok[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c0 = VEC * (tid + NT * j);
-        colok[j] = c0 < a.lda;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const int c = c0 + e;
-            v1[j][e] = (do_grad && c < a.d) ? a.v1[c] : 0.0;
-            v2[j][e] = (do_dot2 && c < a.d) ? a.v2[c] : 0.0;
-            acc[j][e] = 0.0;
-        }
-    }
-    double s1 = 0.0, s2 = 0.0;
-
-    // b values of the next two stages, prefetched by lanes < R of warp 0
-    double b_cur = 0.0, b_nxt = 0.0;
-    auto fetch_b = [&](int s) -> double {
-        if (!use_b || warp != 0 || lane >= R || s >= nst) return 0.0;
-        const long long row = lo + static_cast<long long>(s) * R + lane;
-        return (row < hi) ? __ldg(a.b + row) : 0.0;
-    };
-    b_cur = fetch_b(0);
-    b_nxt = fetch_b(1);
-
-    for (int s = 0; s < nst; ++s) {
-        const int slot = s % nstage;
-        const uint32_t parity = (s / nstage) & 1;
-        const double b_far = fetch_b(s + 2);
-        const long long r0 = lo + static_cast<long long>(s) * R;
-        const int rows = static_cast<int>(min(static_cast<long long>(R), hi - r0));
-        const unsigned char* st = ring + static_cast<size_t>(slot) * stage_bytes;
-
-        mbar_wait(&full_bar[slot], parity);
-
-        double av[R][NV][VEC];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                if (r < rows && colok[j]) {
-                    Vec<T>::load(st + r * row_bytes + static_cast<size_t>(VEC) * (tid + NT * j) * sizeof(T),
-                                 av[r][j]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) av[r][j][e] = 0.0;
-                }
-            }
-        }
-
-        // per-thread partial dot products (two chains per row)
-        double d1[R], d2[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double p1a = 0.0, p1b = 0.0, p2a = 0.0, p2b = 0.0;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    if (((j * VEC + e) & 1) == 0) {
-                        if (do_grad) p1a = fma(av[r][j][e], v1[j][e], p1a);
-                        if (do_dot2) p2a = fma(av[r][j][e], v2[j][e], p2a);
-                    } else {
-                        if (do_grad) p1b = fma(av[r][j][e], v1[j][e], p1b);
-                        if (do_dot2) p2b = fma(av[r][j][e], v2[j][e], p2b);
-                    }
-                }
-            }
-            d1[r] = p1a + p1b;
-            d2[r] = p2a + p2b;
-        }
-        // the stage's bytes now live in registers: hand the slot back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
-
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (do_grad) d1[r] = fos_warp_sum(d1[r]);
-            if (do_dot2) d2[r] = fos_warp_sum(d2[r]);
-        }
-        const int par = s & 1;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (lane == r) {
-                // warp 0 folds -b_i into its partial so that the ordered sum below yields r_i
-                const double bi = (warp == 0) ? b_cur : 0.0;
-                red[par][warp][r][0] = d1[r] - (do_grad ? bi : 0.0);
-                red[par][warp][r][1] = d2[r] - (do_dot2 ? bi : 0.0);
-            }
-        }
-        named_bar_sync(1, NT);
-
-        double r1[R], r2[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const double2 pr = *reinterpret_cast<const double2*>(&red[par][w][r][0]);
-                t1 += pr.x;
-                t2 += pr.y;
-            }
-            r1[r] = t1;
-            r2[r] = t2;
-        }
-        if (do_grad) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] = fma(r1[r], av[r][j][e], acc[j][e]);
-                }
-            }
-        }
-        if (tid == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r < rows) {
-                    s1 = fma(r1[r], r1[r], s1);
-                    s2 = fma(r2[r], r2[r], s2);
-                }
-            }
-        }
-        b_cur = b_nxt;
-        b_nxt = b_far;
-    }
-
-    if (do_grad) {
-        double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c0 = VEC * (tid + NT * j);
-            if (c0 < a.ldv) {
-#pragma unroll
-                for (int e = 0; e < VEC; e += 2) {
-                    if (c0 + e < a.ldv)
-                        *reinterpret_cast<double2*>(out + c0 + e) = make_double2(acc[j][e], acc[j][e + 1]);
-                }
-            }
-        }
-    }
-    if (tid == 0) {
-        a.partial_s[2 * cta + 0] = s1;
-        a.partial_s[2 * cta + 1] = s2;
+    const bool use_b = !(mode & GM_NOB);
+    switch (mode & (GM_GRAD | GM_DOT2)) {
+        case GM_GRAD:
+            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            break;
+        case GM_DOT2:
+            stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            break;
+        default:
+            stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            break;
     }
 }
 
@@ -549,7 +590,7 @@ int fos_launch_grad(fos_design* h, int mode_override) {
         }
         params[1] = &stage_bytes;
         params[2] = &nstage;
-        FOS_CUDA(cudaLaunchKernel(cfg.fn, dim3(h->n_parts), dim3(cfg.nt + 32), params,
+        FOS_CUDA(cudaLaunchKernel(cfg.fn, dim3(h->n_parts), dim3(cfg.nt), params,
                                   static_cast<size_t>(nstage) * stage_bytes, h->stream));
     } else {
         const void* fn = (h->dtype == FOS_F64) ? pick_generic<double>(h->lda) : pick_generic<float>(h->lda);
