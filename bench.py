@@ -166,13 +166,12 @@ def main():
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
 
     t_gen = time.perf_counter()
-    des = DeviceDesign.synthetic(hi - lo, d, np.float64, row0=lo, device=device, **SCENARIO)
-    gen_s = time.perf_counter() - t_gen
     if world > 1:
-        group = multigpu.attach(des, dist)
-        lam = multigpu.lambda_max(des, group)
+        des = multigpu.sharded_synthetic(n, d, dist, device=device, **SCENARIO)
     else:
-        lam = des.lambda_max()
+        des = DeviceDesign.synthetic(n, d, np.float64, device=device, **SCENARIO)
+    gen_s = time.perf_counter() - t_gen
+    lam = des.lambda_max()        # one fused pass; global across ranks (exchange inside the kernel)
     alpha1 = ALPHA_FRAC * lam
 
     # Lipschitz estimate exactly as fista() does it (<= 100 passes), timed separately
@@ -201,15 +200,28 @@ def main():
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
-    x, obj, info = solve(K, True)                     # EXACTLY K timed steps
+    x, obj, info = solve(K, False)                    # EXACTLY K timed steps
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # Same K steps once more with a CUDA-event pair around every gradient-kernel launch (on the
+    # solver stream) for the roofline.  Kept out of the region above because an event between two
+    # launches switches off their programmatic-dependent-launch overlap.
+    _, _, pinfo = solve(K, True)
+    barrier()
     loop_ms = info["loop_ms"]
+    per_rank = None
     if dist is not None:
         import torch
         t = torch.tensor([loop_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         loop_ms = float(t.item())
+        mine = torch.tensor([pinfo["grad_kernel_ms"] / max(pinfo["grad_kernel_launches"], 1),
+                             info["epilogue_ms"] / K, info["exchange_ms"] / K, info["loop_ms"]],
+                            device=f"cuda:{local_rank}", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"grad_kernel_ms_avg": [float(v[0]) for v in allr], "epilogue_ms_per_step": [float(v[1]) for v in allr],
+                    "exchange_wait_ms_per_step": [float(v[2]) for v in allr], "loop_ms": [float(v[3]) for v in allr]}
     value = K / (loop_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the fused gradient pass)
@@ -223,8 +235,8 @@ def main():
     lda = d + (d % 2)
     rows_local = hi - lo
     alg_bytes = rows_local * lda * 8 + rows_local * 8
-    k_launch = max(info["grad_kernel_launches"], 1)
-    k_ms = info["grad_kernel_ms"] / k_launch
+    k_launch = max(pinfo["grad_kernel_launches"], 1)
+    k_ms = pinfo["grad_kernel_ms"] / k_launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     traffic = None
     try:
@@ -236,7 +248,8 @@ def main():
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": k_ms, "launches_timed": k_launch,
-                "kernel_share_of_step": info["grad_kernel_ms"] / info["loop_ms"] if info["loop_ms"] else None,
+                "kernel_share_of_step": pinfo["grad_kernel_ms"] / pinfo["loop_ms"] if pinfo["loop_ms"] else None,
+                "ms_per_step_with_events": pinfo["loop_ms"] / K,
                 "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None}
 
     out = {
@@ -250,14 +263,16 @@ def main():
         "final_objective": float(obj[-1]) if len(obj) else None, "nnz": int(np.count_nonzero(x)),
         "gen_s": gen_s,
     }
+    out["epilogue_ms_per_step"] = info["epilogue_ms"] / K
+    out["exchange_wait_ms_per_step"] = info["exchange_ms"] / K
+    if per_rank is not None:
+        out["per_rank"] = per_rank
     if clocks is not None:
         out["clocks"] = clocks
 
     # ---- end-to-end through the public drop-in API on host buffers (rank-local shard)
-    if not args.no_e2e and world == 1:
-        out["e2e"] = e2e_run(des, alpha1, K, n, d)
-    elif not args.no_e2e:
-        out["e2e"] = multigpu.e2e_run(des, group, alpha1, K, dist)
+    if not args.no_e2e:
+        out["e2e"] = e2e_run(des, alpha1, K, n, d, dist, local_rank)
 
     # ---- CPU baseline on rank 0, N == 1 only
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -279,35 +294,51 @@ def main():
         dist.destroy_process_group()
 
 
-def e2e_run(des, alpha1, K, n, d):
-    """fista(A_host, b_host, ...) through the public API: H2D of A and b from pinned host
-    memory, Lipschitz estimate, K iterations with history, D2H of the iterates -- all timed."""
-    import torch
-    from fastoptsolver_b200 import iterative_solvers as S
-    from fastoptsolver_b200 import design as D
-    # stage the same design in pinned host memory (outside the timed region)
-    A_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
-    b_pin = torch.empty((n,), dtype=torch.float64, pin_memory=True)
-    A_h, b_h = A_pin.numpy(), b_pin.numpy()
-    from fastoptsolver_b200 import _lib
+def e2e_run(des, alpha1, K, n, d, dist, local_rank):
+    """fista(A_host, b_host, ...) through the public API: H2D of this rank's rows of A and b from
+    pinned host memory, (multi-GPU: exchange-window wiring,) Lipschitz estimate, K iterations with
+    history, D2H of the iterates -- all inside the timed region; wall clock, max over ranks."""
     import ctypes as C
-    _lib.check(_lib.load().fos_design_download(des.handle, 0, n, C.c_void_p(A_h.ctypes.data),
+
+    import torch
+    from fastoptsolver_b200 import _lib, multigpu
+    from fastoptsolver_b200 import design as D
+    from fastoptsolver_b200 import iterative_solvers as S
+    rows = des.shape[0]
+    # stage the same numbers in pinned host memory (outside the timed region)
+    A_pin = torch.empty((rows, d), dtype=torch.float64, pin_memory=True)
+    b_pin = torch.empty((rows,), dtype=torch.float64, pin_memory=True)
+    A_h, b_h = A_pin.numpy(), b_pin.numpy()
+    _lib.check(_lib.load().fos_design_download(des.handle, 0, rows, C.c_void_p(A_h.ctypes.data),
                                                C.c_void_p(b_h.ctypes.data)))
     D.clear_cache()
+    if dist is not None:
+        dist.barrier()
     np.random.seed(0)
     t0 = time.perf_counter()
-    x, hist = S.fista(A_h, b_h, "lasso", alpha1, 0.0, max_iter=K, return_history=True)
+    if dist is not None:
+        shard = multigpu.sharded_from_host(A_h, b_h, dist, device=local_rank)
+        x, hist = S.fista(shard, None, "lasso", alpha1, 0.0, max_iter=K, return_history=True)
+    else:
+        shard = None
+        x, hist = S.fista(A_h, b_h, "lasso", alpha1, 0.0, max_iter=K, return_history=True)
     wall = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([wall], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        shard.close()
     info = dict(S.last_run["solver"])
     lip = dict(S.last_run["lipschitz"])
     D.clear_cache()
-    h2d = n * d * 8 + n * 8
+    h2d = rows * d * 8 + rows * 8
     d2h = (K + 1) * d * 8 + K * 8
     return {"value": K / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
             "wall_s": wall, "loop_ms": info["loop_ms"], "lipschitz_ms": lip["gpu_ms"],
-            "lipschitz_iters": lip["iters"],
+            "lipschitz_iters": lip["iters"], "bytes_are": "per rank",
             "what": "fista(A, b, 'lasso', a1, 0, max_iter=K, return_history=True) on pinned host numpy "
-                    "arrays: upload of A+b, power iteration, K iterations, history download"}
+                    "arrays (each rank its row block): upload of A+b, power iteration, K iterations, "
+                    "history download"}
 
 
 def reference_arm(args, world, rank, local_rank, config, K, W):

@@ -53,6 +53,7 @@ class PGResult(C.Structure):
         ("n_iters", C.c_int), ("n_grad_calls", C.c_int), ("n_passes", C.c_int),
         ("stop_reason", C.c_int), ("loop_ms", C.c_float), ("kernel_launches", C.c_int64),
         ("grad_kernel_ms", C.c_float), ("grad_kernel_launches", C.c_int),
+        ("epilogue_ms", C.c_float), ("exchange_ms", C.c_float),
     ]
 
 
@@ -77,9 +78,8 @@ SIGNATURES = {
     "fos_time_grad_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "fos_design_lambda_max": (C.c_int, [C.c_void_p, c_double_p]),
     "fos_comm_window_alloc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "fos_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "fos_comm_set_external": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
-    "fos_comm_partial_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "fos_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fos_comm_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "fos_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, c_double_p]),
     "fos_objective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, c_double_p]),
     "fos_power_iter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, c_double_p, c_int_p, c_float_p]),

@@ -60,6 +60,30 @@ __device__ __forceinline__ void cluster_sum(double (&v)[NS], Shared& sh) {
     }
 }
 
+// ---------------------------------------------------------------- multi-GPU exchange
+// One-shot all-reduce of the (d + 2)-vector [A^T r partial, s1, s2] across the row shards,
+// fused into this kernel: every rank writes its local sum into its own window, publishes an
+// arrival counter into every peer (st.release.sys over NVLink), waits for all peers, and
+// then reads all windows in rank order -- so every rank forms bit-identical sums and the
+// replicated solver state never diverges.  Windows are double-buffered by exchange parity.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld_sys_v2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ size_t win_slot_offset(const EpiArgs& e, unsigned long long epoch) {
+    return static_cast<size_t>(epoch & 1ull) * static_cast<size_t>(e.ldv + FOS_WIN_PAD);
+}
+
 // ordered sum of the per-CTA residual-norm partials; same value in every thread
 __device__ __forceinline__ void load_pass_scalars(const EpiArgs& e, Shared& sh, double& s1, double& s2) {
     if (threadIdx.x < 32) {
@@ -104,6 +128,81 @@ __device__ __forceinline__ double2 column_sum(const EpiArgs& e, int c) {
     return s;
 }
 
+// Publish the local sums and wait for every rank's.  Returns false on timeout (a peer died).
+__device__ __forceinline__ bool peer_exchange(const EpiArgs& e, Shared& sh, bool has_grad, double s1, double s2,
+                                              unsigned long long epoch) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const bool leader = (cluster.block_rank() == 0 && threadIdx.x == 0);
+    double* mine = e.peer.win[e.rank] + win_slot_offset(e, epoch);
+    if (has_grad) {
+        for (int c = 2 * (static_cast<int>(cluster.block_rank()) * FOS_EPI_THREADS + static_cast<int>(threadIdx.x));
+             c < e.ldv; c += 2 * FOS_EPI_THREADS * FOS_EPI_CLUSTER)
+            *reinterpret_cast<double2*>(mine + c) = column_sum(e, c);
+    }
+    if (leader) {
+        mine[e.ldv + 0] = s1;
+        mine[e.ldv + 1] = s2;
+    }
+    __threadfence_system();
+    cluster.sync();
+    if (leader) {
+        for (int p = 0; p < e.world; ++p) st_release_sys(e.peer.flag[p] + e.rank, epoch);
+    }
+    if (threadIdx.x == 0) sh.sc[0] = 1.0;
+    __syncthreads();
+    if (threadIdx.x < e.world) {
+        const unsigned long long* f = e.peer.flag[e.rank] + threadIdx.x;
+        unsigned long long spins = 0;
+        while (ld_acquire_sys(f) < epoch) {
+            if (++spins > (1ull << 28)) {
+                sh.sc[0] = 0.0;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const bool ok = sh.sc[0] != 0.0;
+    __syncthreads();
+    return ok;
+}
+
+// the two pass scalars summed over ranks in rank order (after peer_exchange)
+__device__ __forceinline__ void reduced_scalars(const EpiArgs& e, Shared& sh, unsigned long long epoch, double& s1,
+                                                double& s2) {
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < e.world; ++r) {
+            const double2 v = ld_sys_v2(e.peer.win[r] + win_slot_offset(e, epoch) + e.ldv);
+            a += v.x;
+            b += v.y;
+        }
+        sh.sc[0] = a;
+        sh.sc[1] = b;
+    }
+    __syncthreads();
+    s1 = sh.sc[0];
+    s2 = sh.sc[1];
+    __syncthreads();
+}
+
+// column pair of the gradient summed over CTAs (one GPU) or over ranks (after peer_exchange)
+__device__ __forceinline__ double2 reduced_column(const EpiArgs& e, int c, unsigned long long epoch) {
+    if (e.world <= 1) return column_sum(e, c);
+    double2 s = make_double2(0.0, 0.0);
+    const size_t off = win_slot_offset(e, epoch) + c;
+    double2 v[FOS_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < FOS_MAX_WORLD; ++r)
+        if (r < e.world) v[r] = ld_sys_v2(e.peer.win[r] + off);
+#pragma unroll
+    for (int r = 0; r < FOS_MAX_WORLD; ++r)
+        if (r < e.world) {
+            s.x += v[r].x;
+            s.y += v[r].y;
+        }
+    return s;
+}
+
 __device__ __forceinline__ double prox_point(double y, double t, double g, double a1) {
     double v = __dsub_rn(y, __dmul_rn(t, g));
     if (a1 > 0.0) v = fos_soft_threshold(v, __dmul_rn(t, a1));
@@ -119,6 +218,9 @@ __global__ void __cluster_dims__(FOS_EPI_CLUSTER, 1, 1) __launch_bounds__(FOS_EP
 epilogue_kernel(const EpiArgs e) {
     __shared__ Shared sh;
     cg::cluster_group cluster = cg::this_cluster();
+    // let the next gradient kernel start filling its ring, then wait for this pass's kernel
+    fos_pdl_launch_dependents();
+    fos_pdl_wait();
     const bool leader = (cluster.block_rank() == 0 && threadIdx.x == 0);
     FosCtrl* C = e.ctrl;
 
@@ -129,8 +231,11 @@ epilogue_kernel(const EpiArgs e) {
     // ------------------------------------------------------------------ one-shot ops
     if (e.op == EOP_POWER) {
         if (C->g_mode == GM_SKIP) return;
+        const unsigned long long epoch = (e.world > 1) ? *e.peer.epoch : 0ull;
+        bool comm_ok = true;
+        if (e.world > 1) comm_ok = peer_exchange(e, sh, true, 0.0, 0.0, epoch);
         FOR_MY_COLUMN_PAIRS(c) {
-            const double2 w = column_sum(e, c);
+            const double2 w = reduced_column(e, c, epoch);
             *reinterpret_cast<double2*>(e.g + c) = w;
             if (c < e.d) sums[0] = fma(w.x, w.x, sums[0]);
             if (c + 1 < e.d) sums[0] = fma(w.y, w.y, sums[0]);
@@ -148,17 +253,25 @@ epilogue_kernel(const EpiArgs e) {
             C->L = L;
             C->L_prev = L;
             C->pit = pit + 1;
-            C->g_mode = done ? GM_SKIP : (GM_GRAD | GM_NOB);
+            C->g_mode = (done || !comm_ok) ? GM_SKIP : (GM_GRAD | GM_NOB);
             C->n_passes += 1;
+            if (!comm_ok) C->stop_reason = -1;
+            if (e.world > 1) *e.peer.epoch = epoch + 1;
         }
         return;
     }
     if (e.op == EOP_FG || e.op == EOP_OBJ) {
         double s1, s2;
         load_pass_scalars(e, sh, s1, s2);
+        const unsigned long long epoch = (e.world > 1) ? *e.peer.epoch : 0ull;
+        bool comm_ok = true;
+        if (e.world > 1) {
+            comm_ok = peer_exchange(e, sh, e.op == EOP_FG, s1, s2, epoch);
+            reduced_scalars(e, sh, epoch, s1, s2);
+        }
         if (e.op == EOP_FG) {
             FOR_MY_COLUMN_PAIRS(c) {
-                double2 g = column_sum(e, c);
+                double2 g = reduced_column(e, c, epoch);
                 const double2 x = *reinterpret_cast<const double2*>(e.y + c);
                 if (e.op_bits & 2) {
                     g.x = __dadd_rn(g.x, __dmul_rn(e.op_a2, x.x));
@@ -183,6 +296,8 @@ epilogue_kernel(const EpiArgs e) {
             C->out[1] = s1;
             C->out[2] = s2;
             C->n_passes += 1;
+            C->stop_reason = comm_ok ? 0 : -1;
+            if (e.world > 1) *e.peer.epoch = epoch + 1;
         }
         return;
     }
@@ -199,9 +314,19 @@ epilogue_kernel(const EpiArgs e) {
     const double pend_l2 = C->pend_l2, pend_l1 = C->pend_l1;
     const double t_mom = C->t_mom, prev_step = C->prev_step;
     const unsigned long long pass_t0 = C->pass_t0;
+    const unsigned long long t_epi0 = fos_globaltimer();
 
     double s1, s2;
     load_pass_scalars(e, sh, s1, s2);
+    const unsigned long long epoch = (e.world > 1) ? *e.peer.epoch : 0ull;
+    bool comm_ok = true;
+    unsigned long long t_x0 = 0, t_x1 = 0;
+    if (e.world > 1) {
+        if (leader) t_x0 = fos_globaltimer();
+        comm_ok = peer_exchange(e, sh, phase == PH_GRAD, s1, s2, epoch);
+        if (leader) t_x1 = fos_globaltimer();
+        reduced_scalars(e, sh, epoch, s1, s2);
+    }
 
     // Armijo test of the candidate evaluated by the pass that just ran (:191 / :306 / :101)
     bool accept = false;
@@ -218,7 +343,7 @@ epilogue_kernel(const EpiArgs e) {
     enum { S_GG = 0, S_DX2 = 1, S_L1 = 2, S_XX = 3, S_GD = 4, S_YY = 5 };
     if (phase == PH_GRAD) {
         FOR_MY_COLUMN_PAIRS(c) {
-            double2 g = column_sum(e, c);
+            double2 g = reduced_column(e, c, epoch);
             const double2 y = *reinterpret_cast<const double2*>(e.y + c);
             const double2 xk = *reinterpret_cast<const double2*>(e.xk + c);
             if (a2 > 0.0) {
@@ -400,6 +525,14 @@ epilogue_kernel(const EpiArgs e) {
             if (e.hist.t_hist) e.hist.t_hist[k + 1] = n_tau;
             if (e.hist.step_hist) e.hist.step_hist[k] = this_step;
         }
+        C->epi_ns += fos_globaltimer() - t_epi0;
+        C->xchg_ns += t_x1 - t_x0;
+        if (e.world > 1) *e.peer.epoch = epoch + 1;
+        if (!comm_ok) {  // a peer never arrived: abort the solve, the host reports FOS_ERR_COMM
+            n_phase = PH_DONE;
+            n_gmode = GM_SKIP;
+            n_stop = -1;
+        }
         C->phase = n_phase;
         C->g_mode = n_gmode;
         C->k = n_k;
@@ -454,9 +587,9 @@ int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hi
     e.world = h->world;
     e.rank = h->rank;
     e.peer = h->peer;
-    e.epoch = 0;
-    epilogue_kernel<<<dim3(FOS_EPI_CLUSTER), dim3(FOS_EPI_THREADS), 0, h->stream>>>(e);
-    FOS_CUDA(cudaGetLastError());
+    void* params[1] = {&e};
+    FOS_CUDA(fos_launch_ex(reinterpret_cast<const void*>(&epilogue_kernel), dim3(FOS_EPI_CLUSTER),
+                           dim3(FOS_EPI_THREADS), 0, h->stream, params, h->pdl, 0));
     h->launches++;
     return FOS_OK;
 }

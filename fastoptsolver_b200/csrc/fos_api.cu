@@ -23,6 +23,32 @@ void fos_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fos_last_error(void) { return g_err; }
+
+cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args,
+                          bool pdl, int cluster_x) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    unsigned n = 0;
+    if (pdl) {
+        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 0) {
+        attrs[n].id = cudaLaunchAttributeClusterDimension;
+        attrs[n].val.clusterDim.x = cluster_x;
+        attrs[n].val.clusterDim.y = 1;
+        attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
 extern "C" int fos_abi_version(void) { return FOS_ABI_VERSION; }
 
 extern "C" int fos_device_count(void) {
@@ -77,6 +103,10 @@ static int design_common_init(fos_design* h, long long n, long long d, int dtype
     const int per16 = 16 / elem_size(dtype);
     h->lda = static_cast<int>((d + per16 - 1) / per16 * per16);
     h->ldv = static_cast<int>((d + 1) / 2 * 2);
+    {
+        const char* e = getenv("FOS_NO_PDL");
+        h->pdl = !(e && e[0] == '1');
+    }
     FOS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     FOS_CUDA(cudaEventCreate(&h->ev0));
     FOS_CUDA(cudaEventCreate(&h->ev1));
@@ -118,6 +148,9 @@ static void design_free(fos_design* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    for (int r = 0; r < FOS_MAX_WORLD; ++r)
+        if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->window) cudaFree(h->window);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -370,7 +403,41 @@ static int batch_size(const fos_design* h) {
 // pinned snapshot of the control block.  At most two batches are in flight.
 template <typename DoneFn>
 static int drive_passes(fos_design* h, int eop, const FosHist& hist, long long max_pairs, DoneFn done,
-                        long long* pairs_out) {
+                        long long* pairs_out, bool exact = false) {
+    if (exact) {
+        // The number of passes is known in advance: no polling, no snapshots.  Throttle the
+        // launch queue with one event every 64 pairs.
+        cudaEvent_t ev[2];
+        FOS_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        FOS_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        int status = FOS_OK;
+        long long launched = 0;
+        int chunk = 0;
+        while (launched < max_pairs && status == FOS_OK) {
+            if (chunk >= 2) cudaEventSynchronize(ev[chunk & 1]);
+            for (int i = 0; i < 64 && launched < max_pairs && status == FOS_OK; ++i, ++launched) {
+                const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
+                if (prof) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+                status = fos_launch_grad(h, -1);
+                if (prof) {
+                    cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+                    h->prof_used += 2;
+                }
+                if (status == FOS_OK) status = fos_launch_epilogue(h, eop, 0, hist, 0.0, 0.0, 0);
+            }
+            cudaEventRecord(ev[chunk & 1], h->stream);
+            ++chunk;
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+        if (status == FOS_OK && e != cudaSuccess) {
+            fos_set_error("solver loop failed: %s", cudaGetErrorString(e));
+            status = FOS_ERR_CUDA;
+        }
+        if (pairs_out) *pairs_out = launched;
+        return status;
+    }
     const int B = batch_size(h);
     cudaEvent_t ev[2];
     FOS_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
@@ -462,6 +529,10 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
     FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
     FOS_CUDA(cudaStreamSynchronize(h->stream));
+    if (c->stop_reason < 0) {
+        fos_set_error("multi-GPU exchange timed out: a peer rank never arrived");
+        return FOS_ERR_COMM;
+    }
     *L_out = c->L;
     if (iters_out) *iters_out = c->pit;
     if (gpu_ms_out) FOS_CUDA(cudaEventElapsedTime(gpu_ms_out, h->ev0, h->ev1));
@@ -562,7 +633,8 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
 
     // ---- the loop
     long long max_pairs;
-    if (!p->backtracking && p->tol <= 0.0 && p->tol_ratio <= 0.0)
+    const bool exact = !p->backtracking && p->tol <= 0.0 && p->tol_ratio <= 0.0;
+    if (exact)
         max_pairs = static_cast<long long>(K) + (want_obj ? 1 : 0);  // known exactly
     else
         max_pairs = static_cast<long long>(K) * 1200 + 8;  // tau underflows to 0 well before
@@ -578,13 +650,18 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
     long long pairs = 0;
     if (K > 0)
-        FOS_TRY(drive_passes(h, EOP_PG, hist, max_pairs, [](const FosCtrl& s) { return s.phase == PH_DONE; }, &pairs));
+        FOS_TRY(drive_passes(h, EOP_PG, hist, max_pairs, [](const FosCtrl& s) { return s.phase == PH_DONE; }, &pairs,
+                             exact));
     FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
 
     // ---- results
     FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
     FOS_CUDA(cudaMemcpyAsync(h->vec_host, h->xk, vb, cudaMemcpyDeviceToHost, h->stream));
     FOS_CUDA(cudaStreamSynchronize(h->stream));
+    if (c->stop_reason < 0) {
+        fos_set_error("multi-GPU exchange timed out: a peer rank never arrived");
+        return FOS_ERR_COMM;
+    }
     if (c->phase != PH_DONE && K > 0) {
         fos_set_error("solver stopped in phase %d after %lld passes", c->phase, pairs);
         return FOS_ERR_INVALID;
@@ -606,6 +683,8 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     r->stop_reason = c->stop_reason;
     FOS_CUDA(cudaEventElapsedTime(&r->loop_ms, h->ev0, h->ev1));
     r->kernel_launches = h->launches - launches0;
+    r->epilogue_ms = static_cast<float>(c->epi_ns * 1e-6);
+    r->exchange_ms = static_cast<float>(c->xchg_ns * 1e-6);
     r->grad_kernel_ms = 0.f;
     r->grad_kernel_launches = 0;
     // passes launched after the device reported completion exit immediately: count only the
@@ -657,21 +736,62 @@ extern "C" int fos_prox_elastic_net(const double* v, int64_t len, double tau, do
 }
 
 // ------------------------------------------------------------------------------------------
-// multi-GPU plumbing (peer windows are attached by comm.cu; placeholders until then)
+// multi-GPU plumbing: peer-memory exchange windows (CUDA IPC), used by the fused all-reduce
+// inside the epilogue kernel
 // ------------------------------------------------------------------------------------------
-extern "C" int fos_comm_window_alloc(fos_design*, int, int, void*) {
-    fos_set_error("peer-window exchange not built into this library yet");
-    return FOS_ERR_UNSUPPORTED;
+static size_t window_doubles(const fos_design* h) { return 2 * static_cast<size_t>(h->ldv + FOS_WIN_PAD); }
+
+extern "C" int fos_comm_window_alloc(fos_design* h, int rank, int world, void* ipc_handle_out64) {
+    FOS_REQUIRE(h && ipc_handle_out64, "null pointer argument");
+    FOS_REQUIRE(world >= 1 && world <= FOS_MAX_WORLD, "world size must be in 1..%d", FOS_MAX_WORLD);
+    FOS_REQUIRE(rank >= 0 && rank < world, "rank %d out of range", rank);
+    FOS_REQUIRE(h->window == nullptr, "exchange window already allocated");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    FOS_CUDA(cudaSetDevice(h->device));
+    h->window_bytes = window_doubles(h) * sizeof(double) + (FOS_MAX_WORLD + 8) * sizeof(unsigned long long);
+    FOS_CUDA(cudaMalloc(&h->window, h->window_bytes));
+    FOS_CUDA(cudaMemset(h->window, 0, h->window_bytes));
+    cudaIpcMemHandle_t hd;
+    FOS_CUDA(cudaIpcGetMemHandle(&hd, h->window));
+    memcpy(ipc_handle_out64, &hd, sizeof(hd));
+    h->rank = rank;
+    h->world = 1;  // becomes `world` once the peers are attached
+    h->peer_base[rank] = nullptr;
+    h->peer.win[rank] = static_cast<double*>(h->window);
+    h->peer.flag[rank] = reinterpret_cast<unsigned long long*>(h->peer.win[rank] + window_doubles(h));
+    h->peer.epoch = h->peer.flag[rank] + FOS_MAX_WORLD;
+    // the exchange counter starts at 1 so that a zeroed flag never satisfies a wait
+    unsigned long long one = 1;
+    FOS_CUDA(cudaMemcpy(h->peer.epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
+    return FOS_OK;
 }
-extern "C" int fos_comm_attach(fos_design*, const void*) {
-    fos_set_error("peer-window exchange not built into this library yet");
-    return FOS_ERR_UNSUPPORTED;
+
+extern "C" int fos_comm_attach(fos_design* h, const void* ipc_handles, int world) {
+    FOS_REQUIRE(h && ipc_handles, "null pointer argument");
+    FOS_REQUIRE(h->window != nullptr, "call fos_comm_window_alloc first");
+    FOS_REQUIRE(world >= 1 && world <= FOS_MAX_WORLD && h->rank < world, "bad world size %d", world);
+    FOS_CUDA(cudaSetDevice(h->device));
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(ipc_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == h->rank) continue;
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, hs[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            fos_set_error("cannot map the exchange window of rank %d: %s", r, cudaGetErrorString(e));
+            return FOS_ERR_COMM;
+        }
+        h->peer_base[r] = base;
+        h->peer.win[r] = static_cast<double*>(base);
+        h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
+    }
+    h->world = world;
+    return FOS_OK;
 }
-extern "C" int fos_comm_set_external(fos_design*, int, int) {
-    fos_set_error("external exchange not built into this library yet");
-    return FOS_ERR_UNSUPPORTED;
-}
-extern "C" int fos_comm_partial_dev(fos_design*, double**, int64_t*) {
-    fos_set_error("external exchange not built into this library yet");
-    return FOS_ERR_UNSUPPORTED;
+
+extern "C" int fos_comm_info(const fos_design* h, int* rank, int* world) {
+    FOS_REQUIRE(h, "null design");
+    if (rank) *rank = h->rank;
+    if (world) *world = h->world;
+    return FOS_OK;
 }

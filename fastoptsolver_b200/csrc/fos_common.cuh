@@ -83,6 +83,7 @@ struct FosCtrl {
     int g_mode, phase, k, shrinks, obj_pending, stop_reason, n_grad_calls, n_passes;
     double tau, t_mom, prev_step, trial_t, gy, gd, cand_xx, pend_l2, pend_l1;
     unsigned long long pass_t0;  // %globaltimer at the start of the current pass
+    unsigned long long epi_ns, xchg_ns;  // accumulated epilogue time / time spent waiting for peers
     // ---- power iteration
     double L, L_prev, ptol;
     int pit, pit_max;
@@ -105,11 +106,12 @@ struct FosHist {
 // mapped into all peers through CUDA IPC:  [2 slots][ (ldv + FOS_NSCAL) doubles ] payload,
 // followed by [2 slots][world] 64-bit arrival flags.
 struct FosPeer {
-    int rank, world;
     double* win[8];                // win[r] = rank r's window as mapped in this process
-    unsigned long long* flag[8];   // flag[r] = rank r's flag array
-    unsigned long long epoch;      // monotonically increasing pass counter (host-managed)
+    unsigned long long* flag[8];   // flag[r] = rank r's arrival counters, one per source rank
+    unsigned long long* epoch;     // device-resident exchange counter (identical on all ranks)
 };
+constexpr int FOS_WIN_PAD = 8;     // doubles after the ldv payload: [s1, s2, spare...]
+constexpr int FOS_MAX_WORLD = 8;
 
 // Everything the gradient kernel needs.
 struct GradArgs {
@@ -144,7 +146,6 @@ struct EpiArgs {
     // multi-GPU
     int world, rank;
     FosPeer peer;
-    unsigned long long epoch;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -172,13 +173,13 @@ struct fos_design {
     long long launches = 0;
     // multi-GPU
     int world = 1, rank = 0;
-    int comm_mode = 0;  // 0 none, 1 peer windows, 2 external (host-staged)
-    void* window = nullptr;
+    void* window = nullptr;        // this rank's exchange window (cudaMalloc, IPC-exported)
     size_t window_bytes = 0;
-    void* peer_ptr[8] = {nullptr};
+    void* peer_base[8] = {nullptr};  // cudaIpcOpenMemHandle results (to close on destroy)
     FosPeer peer{};
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
+    bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
     // optional per-launch event timing of the gradient kernel
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
@@ -186,6 +187,8 @@ struct fos_design {
 };
 
 // launchers implemented in the .cu files
+cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args,
+                          bool pdl, int cluster_x);
 int fos_launch_grad(fos_design* h, int mode_override);
 int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hist, double a1,
                         double a2, int bits);
@@ -201,6 +204,12 @@ int fos_launch_repack(const void* src_dev, void* dst_dev, long long rows, int d,
 // device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic stream
+// serialization attribute may start while its predecessor is still running; everything after
+// fos_pdl_wait() sees the predecessor's completed memory.  No-ops for ordinary launches.
+__device__ __forceinline__ void fos_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fos_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long fos_globaltimer() {
     unsigned long long t;

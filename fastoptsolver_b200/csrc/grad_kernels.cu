@@ -291,12 +291,8 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(16) StreamSmem<NW, R> sm;
 
-    const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
-    if ((mode & (GM_GRAD | GM_DOT2 | GM_PROBE)) == 0) return;
-
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, ncta = gridDim.x;
-    if (cta == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
 
     // static contiguous row partition: deterministic summation order
     const long long lo = (a.n * cta) / ncta;
@@ -321,6 +317,20 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         }
     }
     __syncthreads();
+
+    // The ring fill above only touches A, which no kernel ever writes: under programmatic
+    // dependent launch it overlaps the tail of the previous epilogue.  Everything below reads
+    // what that epilogue wrote (pass mode, v1, v2).
+    fos_pdl_launch_dependents();
+    fos_pdl_wait();
+    const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
+    if ((mode & (GM_GRAD | GM_DOT2 | GM_PROBE)) == 0) {
+        // nothing to do (solver already finished): drain the copies in flight before exiting
+        if (tid == 0)
+            for (int s = 0; s < nstage && s < nst; ++s) mbar_wait(&sm.full_bar[s], 0);
+        return;
+    }
+    if (cta == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
 
     // ===== consumers =====
     if (mode & GM_PROBE) {
@@ -373,6 +383,8 @@ grad_generic_kernel(GradArgs a) {
     __shared__ double wacc[GEN_WARPS][J * 32];
     __shared__ double wsc[GEN_WARPS][2];
 
+    fos_pdl_launch_dependents();
+    fos_pdl_wait();
     const int mode = (a.mode_override >= 0) ? a.mode_override : a.ctrl->g_mode;
     if ((mode & (GM_GRAD | GM_DOT2)) == 0) return;
     const bool do_grad = mode & GM_GRAD;
@@ -501,11 +513,14 @@ StreamCfg make_cfg() {
 }
 
 bool pick_stream_cfg(int dtype, int lda, StreamCfg* out) {
+    // FOS_ROWS_X2=1 doubles the rows handled per barrier (A/B switch for tuning)
+    const char* e = getenv("FOS_ROWS_X2");
+    const bool x2 = e && e[0] == '1';
     if (dtype == FOS_F64) {
         if (lda <= 512) *out = make_cfg<double, 256, 2, 8>();
         else if (lda <= 1024) *out = make_cfg<double, 256, 4, 4>();
-        else if (lda <= 2048) *out = make_cfg<double, 256, 8, 2>();
-        else if (lda <= 4096) *out = make_cfg<double, 256, 16, 1>();
+        else if (lda <= 2048) *out = x2 ? make_cfg<double, 256, 8, 4>() : make_cfg<double, 256, 8, 2>();
+        else if (lda <= 4096) *out = x2 ? make_cfg<double, 256, 16, 2>() : make_cfg<double, 256, 16, 1>();
         else if (lda <= 8192) *out = make_cfg<double, 512, 16, 1>();
         else return false;
     } else {
@@ -590,11 +605,11 @@ int fos_launch_grad(fos_design* h, int mode_override) {
         }
         params[1] = &stage_bytes;
         params[2] = &nstage;
-        FOS_CUDA(cudaLaunchKernel(cfg.fn, dim3(h->n_parts), dim3(cfg.nt), params,
-                                  static_cast<size_t>(nstage) * stage_bytes, h->stream));
+        FOS_CUDA(fos_launch_ex(cfg.fn, dim3(h->n_parts), dim3(cfg.nt), static_cast<size_t>(nstage) * stage_bytes,
+                               h->stream, params, h->pdl, 0));
     } else {
         const void* fn = (h->dtype == FOS_F64) ? pick_generic<double>(h->lda) : pick_generic<float>(h->lda);
-        FOS_CUDA(cudaLaunchKernel(fn, dim3(h->n_parts), dim3(GEN_WARPS * 32), params, 0, h->stream));
+        FOS_CUDA(fos_launch_ex(fn, dim3(h->n_parts), dim3(GEN_WARPS * 32), 0, h->stream, params, h->pdl, 0));
     }
     h->launches++;
     return FOS_OK;

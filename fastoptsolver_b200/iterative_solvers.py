@@ -135,6 +135,7 @@ def _run(des, *, scheme, alpha1, alpha2, obj_terms, delta, backtracking, eta, st
         "iters": it, "grad_calls": r.n_grad_calls, "passes": r.n_passes, "stop_reason": r.stop_reason,
         "loop_ms": r.loop_ms, "kernel_launches": r.kernel_launches,
         "grad_kernel_ms": r.grad_kernel_ms, "grad_kernel_launches": r.grad_kernel_launches,
+        "epilogue_ms": r.epilogue_ms, "exchange_ms": r.exchange_ms,
     }
     return x, it, xh, oh, th, sh
 

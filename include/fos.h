@@ -111,11 +111,8 @@ int fos_design_lambda_max(fos_design* h, double* out);
  * torch.distributed.all_gather), and maps the peers' windows with fos_comm_attach; the
  * epilogue kernel then reduces across NVLink in fixed rank order inside the same launch. */
 int fos_comm_window_alloc(fos_design* h, int rank, int world, void* ipc_handle_out64);
-int fos_comm_attach(fos_design* h, const void* ipc_handles /* world x 64 bytes */);
-/* Host-staged mode (any backend, used by the gloo tests and as NCCL fallback): the pass is
- * split so that the caller can all-reduce the (d+2) partial itself between the halves. */
-int fos_comm_set_external(fos_design* h, int rank, int world);
-int fos_comm_partial_dev(fos_design* h, double** partial_dev, int64_t* count);
+int fos_comm_attach(fos_design* h, const void* ipc_handles /* world x 64 bytes */, int world);
+int fos_comm_info(const fos_design* h, int* rank, int* world);
 
 /* ---- one-shot operators ----------------------------------------------------------------
  * fos_grad: loss = 0.5||Ax-b||^2 (+0.5 a2 ||x||^2), g = A^T(Ax-b) (+a2 x), A read ONCE.
@@ -177,6 +174,10 @@ typedef struct fos_pg_result {
      * launch of the loop (on the solver stream), summed */
     float grad_kernel_ms;
     int grad_kernel_launches;
+    /* device-side (%globaltimer) totals over the loop: time inside the epilogue kernel, and the
+     * part of it spent publishing to / waiting for the peer ranks (0 on one GPU) */
+    float epilogue_ms;
+    float exchange_ms;
 } fos_pg_result;
 
 int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r);

@@ -156,7 +156,10 @@ def check_case(out, spec, name, key, rtol, *, lbfgs_trace_rtol=None, check_signs
             assert err.max() <= rtol, f"{name}:{key} objective trace rel {err.max():.3e}"
     if kind == "ista":
         assert len(out["ht"]) == len(ref["ht"]) and len(out["hdelta"]) == len(ref["hdelta"])
-        np.testing.assert_allclose(out["ht"], ref["ht"], rtol=rtol)
+        # step sizes are comparable up to the first rounding-decided line search (see above)
+        ref_ls = list(ref["ls_iters"])
+        cut = next((i for i, v in enumerate(ref_ls) if v > 20), len(ref["ht"]) - 1)
+        np.testing.assert_allclose(out["ht"][: cut + 1], ref["ht"][: cut + 1], rtol=rtol)
         # delta_k = ||x_{k+1} - x_k|| is a difference of iterates: absolute tolerance on the
         # scale of the iterates (a converged run has deltas at rounding level)
         np.testing.assert_allclose(out["hdelta"], ref["hdelta"], rtol=1e-7,

@@ -1,0 +1,81 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the row-sharded path -- shard
+bounds, the handle exchange, and the algebra the fused all-reduce relies on
+(sum over shards of A_g^T(A_g y - b_g) == A^T(Ay - b); the oracle stands in for the kernel)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from fastoptsolver_b200 import multigpu
+        # 1. handle exchange: every rank ends up with everybody's 64 bytes, in rank order
+        mine = bytes([rank]) * 64
+        got = multigpu.exchange_bytes(mine, dist)
+        assert got == [bytes([r]) * 64 for r in range(world)]
+        # 2. sharded gradient algebra on an uneven split
+        rng = np.random.default_rng(0)
+        n, d = 1001, 17
+        A = rng.standard_normal((n, d))
+        b = rng.standard_normal(n)
+        y = rng.standard_normal(d)
+        lo, hi = multigpu.shard_bounds(n, rank, world)
+        loss_l, g_l = oracle.smooth_value_and_grad(y, A[lo:hi], b[lo:hi])
+        t = torch.from_numpy(np.concatenate([g_l, [loss_l]]))
+        dist.all_reduce(t)
+        loss, g = oracle.smooth_value_and_grad(y, A, b)
+        np.testing.assert_allclose(t.numpy()[:-1], g, rtol=1e-12)
+        np.testing.assert_allclose(t.numpy()[-1], loss, rtol=1e-12)
+        q.put((rank, "ok", (lo, hi)))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, f"fail: {e!r}", None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_rows():
+    from fastoptsolver_b200.multigpu import shard_bounds
+    for n in (1, 7, 1000, 1_000_000):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_bounds(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == ["ok", "ok"], res
+    assert res[0][2] == (0, 500) and res[1][2] == (500, 1001)
