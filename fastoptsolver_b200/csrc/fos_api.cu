@@ -569,7 +569,9 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     const int K = p->max_iter;
     const int d = h->d;
     const bool want_hist = p->want_history != 0;
-    const bool want_obj = want_hist && p->scheme != FOS_SCHEME_ISTA;
+    // ISTA records no objective in the reference (iterative_solvers.py:83); the engine gets it
+    // for free (second dot of the same pass) and the drop-in exposes it as an extra.
+    const bool want_obj = want_hist;
     const long long launches0 = h->launches;
 
     // ---- per-solve device arrays

@@ -171,12 +171,15 @@ def ista(
                                return_history)
     x0 = np.asarray(x0, dtype=np.float64)
     step0 = t_init_factor / L
-    x, it, xh, _, th, sh = _run(
-        g.design, scheme=_lib.SCHEME_ISTA, alpha1=prox_h.alpha1, alpha2=grad_g.alpha2, obj_terms=0, delta=0.0,
+    terms = (1 if prox_h.alpha1 > 0 else 0) | (2 if grad_g.alpha2 > 0 else 0)
+    x, it, xh, oh, th, sh = _run(
+        g.design, scheme=_lib.SCHEME_ISTA, alpha1=prox_h.alpha1, alpha2=grad_g.alpha2, obj_terms=terms, delta=0.0,
         backtracking=backtracking, eta=eta, step0=step0, max_iter=max_iter, tol=tol, tol_ratio=0.0,
         adaptive_restart=False, restart_threshold=1.0, want_history=return_history, x0=x0)
     if not return_history:
         return x
+    # extra (not part of the reference's log): objective of x_1..x_k, free by-product of the pass
+    last_run["ista_obj"] = [np.float64(v) for v in oh[:it]]
     log = {"x": [xh[i].copy() for i in range(it + 1)],
            "t": [step0] + [float(v) for v in th[1: it + 1]],
            "delta": [np.float64(v) for v in sh[:it]]}

@@ -243,3 +243,30 @@ def test_large_size_properties():
     loss_blk, g_blk = des_blk.grad(x)
     assert abs(loss_blk - loss_ref) <= 1e-12 * loss_ref and harness.rel_err(g_blk, g_ref) <= 1e-12
     des.close()
+
+
+def test_sweep_driver_small():
+    """The notebook replacement: one scenario, all 19 variants, CSV out; ISTA's by-product
+    objective equals compute_objective of its iterates."""
+    import tempfile
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200 import sweep
+    from fastoptsolver_b200.design import DeviceDesign
+    from fastoptsolver_b200.operators import ista_callables
+    des = DeviceDesign.synthetic(5000, 40, seed=0, noise_std=0.5, rho1=0.5, rho2=0.7)
+    traces, timing, meta = sweep.run_scenario(des, max_iter=30)
+    assert set(traces) == {"L-BFGS", "ISTA", "FISTA", "FISTA-delta"}
+    assert len(traces["FISTA"]) == 6 and len(traces["ISTA"]) == 6 and len(traces["L-BFGS"]) == 2
+    sub = sweep.suboptimality(traces)
+    assert all(v >= 0 for c in sub.values() for tr in c.values() for v in tr)
+    with tempfile.TemporaryDirectory() as tmp:
+        sweep.write_csv(os.path.join(tmp, "x.csv"), sub)
+        assert os.path.getsize(os.path.join(tmp, "x.csv")) > 1000
+    a1 = meta["alpha1"]
+    np.random.seed(0)
+    L = S.estimate_lipschitz(des)
+    g, grad_g, prox_h = ista_callables(des, None, a1, 0.0)
+    _, log = S.ista(np.zeros(40), g, grad_g, prox_h, L, max_iter=10, return_history=True)
+    direct = [des.objective(x, 1, a1, 0.0) for x in log["x"][1:]]
+    np.testing.assert_allclose(S.last_run["ista_obj"], direct, rtol=1e-12)
+    des.close()
