@@ -87,6 +87,14 @@ SIGNATURES = {
     "fos_prox_elastic_net": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                        C.c_int]),
     "fos_prox_grad": (C.c_int, [C.c_void_p, C.POINTER(PGParams), C.POINTER(PGResult)]),
+    "fos_gram_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fos_gram_destroy": (C.c_int, [C.c_void_p]),
+    "fos_gram_info": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_float_p, c_int_p]),
+    "fos_gram_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fos_gram_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fos_gram_set_btb": (C.c_int, [C.c_void_p, C.c_double]),
+    "fos_gram_path_fista": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                      C.c_void_p, c_float_p, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

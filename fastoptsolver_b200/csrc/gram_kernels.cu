@@ -1,0 +1,520 @@
+// gram_kernels.cu -- Gram-matrix mode for n >> d and the batched multi-lambda path
+// (north_star item 4; BASELINE.json configs[4]).  These are the only dense contractions on the
+// path and the only place tensor cores are used: fp64 DMMA (mma.sync.m8n8k4.f64 -- tcgen05 has
+// no f64 kind).
+//
+//   gram_syrk_kernel   G_partial[s] = A[k-range s]^T A[k-range s]   (upper-triangular 128x128 tiles)
+//   gram_reduce_kernel G = sum_s G_partial[s], mirrored to the lower triangle (fixed order)
+//   path_step_kernel   one FISTA iteration for Lambda penalties at once:
+//                      Grad = G Y - c 1^T (+a2 Y);  X+ = prox(Y - tau Grad, tau a1[l]);
+//                      Y+ = X+ + beta (X+ - X)          (iterative_solvers.py:173-221, batched)
+//   path_obj_kernel    per-column  0.5 x^T G x - c^T x + 0.5 b^T b (+0.5 a2 |x|^2) (+a1 |x|_1)
+//
+// Operands are staged with cp.async (16 B, L1 bypass) into a 4-stage shared-memory ring whose
+// row pitch is padded by 4 doubles, which makes every DMMA fragment load conflict free.
+// Bound: the fp64 tensor pipe (n d^2 FMA for the build, d^2 Lambda per path iteration).
+#include <math.h>
+
+#include <algorithm>
+
+#include "fos_common.cuh"
+
+namespace {
+
+constexpr int GT = 128;       // Gram tile edge
+constexpr int GKB = 16;       // rows of A per pipeline stage
+constexpr int GLD = GT + 4;   // padded shared row pitch (doubles)
+constexpr int GSTAGES = 4;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills (used for rows past the end)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct SyrkArgs {
+    const double* A;
+    long long n;
+    int lda;
+    int nb;                  // d / 128
+    int ntiles;              // nb (nb+1) / 2
+    long long rows_per_split;  // multiple of GKB
+    double* W;               // [nsplit][dpad][dpad]
+    long long dpad;
+};
+
+__global__ void __launch_bounds__(256, 1) gram_syrk_kernel(const SyrkArgs g) {
+    extern __shared__ __align__(16) double smem[];  // [GSTAGES][2][GKB][GLD]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x / g.ntiles;
+    int rem = blockIdx.x % g.ntiles, bi = 0;
+    while (rem >= g.nb - bi) {
+        rem -= g.nb - bi;
+        ++bi;
+    }
+    const int bj = bi + rem;
+    const long long k_lo = split * g.rows_per_split;
+    const long long k_hi = min(g.n, k_lo + g.rows_per_split);
+    const int nst = static_cast<int>((k_hi - k_lo + GKB - 1) / GKB);
+
+    // cp.async assignment: 2 operands x 16 rows x 64 chunks of 16 B = 2048 chunks, 8 per thread
+    auto issue = [&](int st) {
+        if (st < nst) {
+            double* base = smem + static_cast<size_t>(st % GSTAGES) * (2 * GKB * GLD);
+            const long long r0 = k_lo + static_cast<long long>(st) * GKB;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int chunk = tid + 256 * q;       // 0..2047
+                const int op = chunk >> 10;            // 0: column block bi, 1: column block bj
+                const int row = (chunk >> 6) & 15;
+                const int c16 = chunk & 63;            // 16-byte chunk within the 1 KB row segment
+                const long long r = r0 + row;
+                const bool ok = r < k_hi;
+                const double* src = g.A + (ok ? r : k_lo) * g.lda + (op ? bj : bi) * GT + c16 * 2;
+                cp_async16(base + (op * GKB + row) * GLD + c16 * 2, src, ok ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int wi = warp >> 1, wj = warp & 1;  // 4 x 2 warps, warp tile 32 (i) x 64 (j)
+    const int fk = lane & 3, fc = lane >> 2;
+
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; ++s) issue(s);
+    for (int s = 0; s < nst; ++s) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();
+        issue(s + GSTAGES - 1);
+        const double* tI = smem + static_cast<size_t>(s % GSTAGES) * (2 * GKB * GLD);
+        const double* tJ = tI + GKB * GLD;
+#pragma unroll
+        for (int k4 = 0; k4 < GKB; k4 += 4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = tI[(k4 + fk) * GLD + wi * 32 + i * 8 + fc];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = tJ[(k4 + fk) * GLD + wj * 64 + j * 8 + fc];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    double* out = g.W + static_cast<size_t>(split) * g.dpad * g.dpad;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long row = static_cast<long long>(bi) * GT + wi * 32 + i * 8 + fc;
+            const long long col = static_cast<long long>(bj) * GT + wj * 64 + j * 8 + fk * 2;
+            *reinterpret_cast<double2*>(out + row * g.dpad + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+}
+
+// G[i][j] = sum_s W[s][min-tile order] for the upper tile triangle, mirrored below it
+__global__ void gram_reduce_kernel(const double* __restrict__ W, double* __restrict__ G, long long dpad,
+                                   int nsplit) {
+    const long long i = blockIdx.y;
+    const long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= dpad) return;
+    const long long ti = i / GT, tj = j / GT;
+    long long si = i, sj = j;
+    if (ti > tj) {  // below the tile diagonal: read the transposed element
+        si = j;
+        sj = i;
+    }
+    double s = 0.0;
+    for (int p = 0; p < nsplit; ++p) s += W[static_cast<size_t>(p) * dpad * dpad + si * dpad + sj];
+    G[i * dpad + j] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched path iteration: out tile 128 (i) x 64 (l), K chunks of 16
+// ------------------------------------------------------------------------------------------
+constexpr int PM = 128, PN = 64, PK = 16, PLD = PK + 4, PSTAGES = 4;
+
+struct PathArgs {
+    const double* G;      // [d][d] row-major, symmetric
+    const double* c;      // A^T b
+    const double* Yin;    // [Lpad][d]
+    double* Yout;         // [Lpad][d]
+    double* X;            // [Lpad][d]  (in: x_k, out: x_{k+1})
+    const double* alpha1; // [Lpad]
+    double alpha2, tau, beta;
+    int d, Lpad;
+    int mode;             // 0: FISTA step, 1: objective partials of X (Yin = X)
+    double* obj_part;     // [d/128][Lpad][4]: x^T G x, c^T x, |x|_1, |x|^2 partials per i-block
+};
+
+__global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
+    extern __shared__ __align__(16) double smem[];  // [PSTAGES][(PM+PN)][PLD]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.x * PM, l0 = blockIdx.y * PN;
+    const int nst = p.d / PK;
+
+    auto issue = [&](int st) {
+        if (st < nst) {
+            double* base = smem + static_cast<size_t>(st % PSTAGES) * ((PM + PN) * PLD);
+            const int k0 = st * PK;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int chunk = tid + 256 * q;  // (128 + 64) rows x 8 chunks = 1536
+                const int row = chunk >> 3, c16 = chunk & 7;
+                const double* src = (row < PM) ? p.G + static_cast<size_t>(i0 + row) * p.d + k0 + c16 * 2
+                                               : p.Yin + static_cast<size_t>(l0 + row - PM) * p.d + k0 + c16 * 2;
+                cp_async16(base + row * PLD + c16 * 2, src, 16);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wi = warp >> 1, wl = warp & 1;  // 4 x 2 warps, warp tile 32 (i) x 32 (l)
+    const int fk = lane & 3, fc = lane >> 2;
+
+#pragma unroll
+    for (int s = 0; s < PSTAGES - 1; ++s) issue(s);
+    for (int s = 0; s < nst; ++s) {
+        cp_async_wait<PSTAGES - 2>();
+        __syncthreads();
+        issue(s + PSTAGES - 1);
+        const double* tG = smem + static_cast<size_t>(s % PSTAGES) * ((PM + PN) * PLD);
+        const double* tY = tG + PM * PLD;
+#pragma unroll
+        for (int k4 = 0; k4 < PK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = tG[(wi * 32 + i * 8 + fc) * PLD + k4 + fk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = tY[(wl * 32 + j * 8 + fc) * PLD + k4 + fk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    if (p.mode == 0) {
+        // fused FISTA update on the tile (same roundings as the single-lambda epilogue)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = i0 + wi * 32 + i * 8 + fc;
+                    const int l = l0 + wl * 32 + j * 8 + fk * 2 + e;
+                    const size_t idx = static_cast<size_t>(l) * p.d + col;
+                    const double y = p.Yin[idx], xk = p.X[idx];
+                    double g = __dsub_rn(acc[i][j][e], p.c[col]);
+                    if (p.alpha2 > 0.0) g = __dadd_rn(g, __dmul_rn(p.alpha2, y));
+                    double v = __dsub_rn(y, __dmul_rn(p.tau, g));
+                    const double a1 = p.alpha1[l];
+                    if (a1 > 0.0) v = fos_soft_threshold(v, __dmul_rn(p.tau, a1));
+                    p.X[idx] = v;
+                    p.Yout[idx] = __dadd_rn(v, __dmul_rn(p.beta, __dsub_rn(v, xk)));
+                }
+    } else {
+        // objective partials over this CTA's 128 columns: per l, sum_i x_i (Gx)_i etc.
+        __shared__ double part[8][32][4];  // [warp][l within warp tile][4 sums]
+        double sums[4][2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sums[j][e][q] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = i0 + wi * 32 + i * 8 + fc;
+                    const int l = l0 + wl * 32 + j * 8 + fk * 2 + e;
+                    const double x = p.Yin[static_cast<size_t>(l) * p.d + col];
+                    sums[j][e][0] = fma(x, acc[i][j][e], sums[j][e][0]);
+                    sums[j][e][1] = fma(x, p.c[col], sums[j][e][1]);
+                    sums[j][e][2] += fabs(x);
+                    sums[j][e][3] = fma(x, x, sums[j][e][3]);
+                }
+        // reduce over the 8 lanes that share fk (lane>>2 varies): xor 4, 8, 16
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double v = sums[j][e][q];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (fc == 0) part[warp][j * 8 + fk * 2 + e][q] = v;
+                }
+        __syncthreads();
+        // combine the 4 i-warps of each l half, fixed order; 64 l x 4 sums = 256 threads
+        const int l_loc = tid >> 2, q = tid & 3;
+        const int wl2 = l_loc >> 5, lw = l_loc & 31;
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t += part[w * 2 + wl2][lw][q];
+        p.obj_part[(static_cast<size_t>(blockIdx.x) * p.Lpad + l0 + l_loc) * 4 + q] = t;
+    }
+}
+
+__global__ void path_obj_finish_kernel(const double* __restrict__ part, int nblk, int Lpad, const double* alpha1,
+                                       double alpha2, double half_bb, double* __restrict__ obj) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= Lpad) return;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = 0; b < nblk; ++b)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] += part[(static_cast<size_t>(b) * Lpad + l) * 4 + q];
+    double v = 0.5 * s[0] - s[1] + half_bb;
+    if (alpha2 > 0.0) v += 0.5 * alpha2 * s[3];
+    if (alpha1[l] > 0.0) v += alpha1[l] * s[2];
+    obj[l] = v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct fos_gram {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int d = 0;
+    double* G = nullptr;    // [d][d]
+    double* c = nullptr;    // [d]
+    double bb = 0.0;        // b^T b
+    float build_ms = 0.f;
+    int nsplit = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static void gram_free(fos_gram* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->G) cudaFree(g->G);
+    if (g->c) cudaFree(g->c);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    cudaGetLastError();
+    delete g;
+}
+
+extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
+    FOS_REQUIRE(h && out, "null pointer argument");
+    FOS_REQUIRE(h->dtype == FOS_F64, "Gram mode needs float64 storage");
+    FOS_REQUIRE(h->d % GT == 0, "Gram mode needs d to be a multiple of %d (got %d)", GT, h->d);
+    FOS_CUDA(cudaSetDevice(h->device));
+    fos_gram* g = new fos_gram();
+    g->device = h->device;
+    g->d = h->d;
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        FOS_CUDA(cudaEventCreate(&g->ev0));
+        FOS_CUDA(cudaEventCreate(&g->ev1));
+        const long long d = h->d;
+        FOS_CUDA(cudaMalloc(&g->G, static_cast<size_t>(d) * d * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&g->c, static_cast<size_t>(d) * sizeof(double)));
+        // c = A^T b and b^T b from one pass of the streaming kernel with x = 0: g = -A^T b
+        std::vector<double> zero(h->d, 0.0), gneg(h->d);
+        double half_bb = 0.0;
+        FOS_TRY(fos_grad(h, zero.data(), 0.0, gneg.data(), &half_bb));
+        for (double& v : gneg) v = -v;
+        g->bb = 2.0 * half_bb;
+        FOS_CUDA(cudaMemcpy(g->c, gneg.data(), static_cast<size_t>(d) * sizeof(double), cudaMemcpyHostToDevice));
+
+        SyrkArgs a{};
+        a.A = static_cast<const double*>(h->A);
+        a.n = h->n;
+        a.lda = h->lda;
+        a.nb = h->d / GT;
+        a.ntiles = a.nb * (a.nb + 1) / 2;
+        a.dpad = d;
+        // split the rows so that tiles x splits fills whole waves of SMs
+        int best = 1;
+        double best_eff = 0.0;
+        const long long max_split = std::max<long long>(1, std::min<long long>(16, h->n / (4 * GKB)));
+        for (int s = 1; s <= max_split; ++s) {
+            const long long units = static_cast<long long>(a.ntiles) * s;
+            const long long waves = (units + h->sm_count - 1) / h->sm_count;
+            const double eff = static_cast<double>(units) / (waves * h->sm_count);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = s;
+            }
+        }
+        g->nsplit = best;
+        long long rps = (h->n + best - 1) / best;
+        rps = (rps + GKB - 1) / GKB * GKB;
+        a.rows_per_split = rps;
+        double* W = nullptr;
+        FOS_CUDA(cudaMalloc(&W, static_cast<size_t>(best) * d * d * sizeof(double)));
+        a.W = W;
+        const size_t smem = static_cast<size_t>(GSTAGES) * 2 * GKB * GLD * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e == cudaSuccess) {
+            cudaEventRecord(g->ev0, g->stream);
+            gram_syrk_kernel<<<dim3(a.ntiles * best), dim3(256), smem, g->stream>>>(a);
+            gram_reduce_kernel<<<dim3(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d)), dim3(256), 0,
+                                 g->stream>>>(W, g->G, d, best);
+            cudaEventRecord(g->ev1, g->stream);
+            e = cudaStreamSynchronize(g->stream);
+        }
+        cudaFree(W);
+        if (e != cudaSuccess) {
+            fos_set_error("Gram build failed: %s", cudaGetErrorString(e));
+            return FOS_ERR_CUDA;
+        }
+        FOS_CUDA(cudaEventElapsedTime(&g->build_ms, g->ev0, g->ev1));
+        return FOS_OK;
+    };
+    int st = body();
+    if (st != FOS_OK) {
+        gram_free(g);
+        return st;
+    }
+    *out = g;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_destroy(fos_gram* g) {
+    gram_free(g);
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_info(const fos_gram* g, int* d, double* btb, float* build_ms, int* nsplit) {
+    FOS_REQUIRE(g, "null gram handle");
+    if (d) *d = g->d;
+    if (btb) *btb = g->bb;
+    if (build_ms) *build_ms = g->build_ms;
+    if (nsplit) *nsplit = g->nsplit;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_pointers(fos_gram* g, double** G_dev, double** c_dev) {
+    FOS_REQUIRE(g, "null gram handle");
+    if (G_dev) *G_dev = g->G;
+    if (c_dev) *c_dev = g->c;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_download(fos_gram* g, double* G_out, double* c_out) {
+    FOS_REQUIRE(g, "null gram handle");
+    FOS_CUDA(cudaSetDevice(g->device));
+    const size_t d = g->d;
+    if (G_out) FOS_CUDA(cudaMemcpy(G_out, g->G, d * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (c_out) FOS_CUDA(cudaMemcpy(c_out, g->c, d * sizeof(double), cudaMemcpyDeviceToHost));
+    return FOS_OK;
+}
+
+// replace G and c (after an all-reduce over row-sharded ranks done by the caller)
+extern "C" int fos_gram_set_btb(fos_gram* g, double btb) {
+    FOS_REQUIRE(g, "null gram handle");
+    g->bb = btb;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_path_fista(fos_gram* g, const double* alphas1, int n_lambda, double alpha2, double step,
+                                   int max_iter, double* X_out, double* obj_out, float* loop_ms, int64_t* launches) {
+    FOS_REQUIRE(g && alphas1 && n_lambda >= 1 && max_iter >= 0 && step > 0.0, "bad argument");
+    FOS_CUDA(cudaSetDevice(g->device));
+    const int d = g->d;
+    const int Lpad = (n_lambda + PN - 1) / PN * PN;
+    const size_t mat = static_cast<size_t>(Lpad) * d;
+    double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {Y0, Y1, X, a1, part, obj})
+            if (q) cudaFree(q);
+    };
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaMalloc(&Y0, mat * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&Y1, mat * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&X, mat * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&a1, Lpad * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&part, static_cast<size_t>(d / PM) * Lpad * 4 * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&obj, Lpad * sizeof(double)));
+        FOS_CUDA(cudaMemsetAsync(Y0, 0, mat * sizeof(double), g->stream));
+        FOS_CUDA(cudaMemsetAsync(Y1, 0, mat * sizeof(double), g->stream));
+        FOS_CUDA(cudaMemsetAsync(X, 0, mat * sizeof(double), g->stream));
+        std::vector<double> al(Lpad, 0.0);
+        for (int l = 0; l < n_lambda; ++l) al[l] = alphas1[l];
+        FOS_CUDA(cudaMemcpyAsync(a1, al.data(), Lpad * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+        const size_t smem = static_cast<size_t>(PSTAGES) * (PM + PN) * PLD * sizeof(double);
+        FOS_CUDA(cudaFuncSetAttribute(path_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        PathArgs p{};
+        p.G = g->G;
+        p.c = g->c;
+        p.X = X;
+        p.alpha1 = a1;
+        p.alpha2 = alpha2;
+        p.tau = step;
+        p.d = d;
+        p.Lpad = Lpad;
+        p.obj_part = part;
+        const dim3 grid(d / PM, Lpad / PN);
+        double t_prev = 1.0;
+        int64_t n_launch = 0;
+        FOS_CUDA(cudaEventRecord(g->ev0, g->stream));
+        for (int k = 0; k < max_iter; ++k) {
+            // Nesterov momentum of fista (iterative_solvers.py:219-221), same for every column
+            const double t_cur = 0.5 * (1.0 + sqrt(1.0 + 4.0 * (t_prev * t_prev)));
+            p.beta = (t_prev - 1.0) / t_cur;
+            t_prev = t_cur;
+            p.mode = 0;
+            p.Yin = (k & 1) ? Y1 : Y0;
+            p.Yout = (k & 1) ? Y0 : Y1;
+            path_step_kernel<<<grid, dim3(256), smem, g->stream>>>(p);
+            ++n_launch;
+        }
+        FOS_CUDA(cudaEventRecord(g->ev1, g->stream));
+        p.mode = 1;
+        p.Yin = X;
+        p.Yout = nullptr;
+        path_step_kernel<<<grid, dim3(256), smem, g->stream>>>(p);
+        path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, d / PM, Lpad, a1, alpha2,
+                                                                                   0.5 * g->bb, obj);
+        n_launch += 2;
+        FOS_CUDA(cudaGetLastError());
+        FOS_CUDA(cudaStreamSynchronize(g->stream));
+        if (X_out)
+            FOS_CUDA(cudaMemcpy(X_out, X, static_cast<size_t>(n_lambda) * d * sizeof(double), cudaMemcpyDeviceToHost));
+        if (obj_out) FOS_CUDA(cudaMemcpy(obj_out, obj, n_lambda * sizeof(double), cudaMemcpyDeviceToHost));
+        if (loop_ms) FOS_CUDA(cudaEventElapsedTime(loop_ms, g->ev0, g->ev1));
+        if (launches) *launches = n_launch;
+        return FOS_OK;
+    };
+    const int st = body();
+    cleanup();
+    return st;
+}

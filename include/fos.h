@@ -182,6 +182,25 @@ typedef struct fos_pg_result {
 
 int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r);
 
+/* ---- Gram-matrix mode (n >> d) and the batched regularisation path --------------------------
+ * New capability (north_star item 4; no counterpart in the reference, which re-reads A every
+ * iteration): G = A^T A, c = A^T b, b^T b are built once with fp64 tensor-core MMA, after
+ * which a FISTA iteration for Lambda penalties at once is one d x d x Lambda contraction
+ *   Grad = G Y - c 1^T (+alpha2 Y)   (== A^T(A y - b) + alpha2 y of iterative_solvers.py:173-175)
+ * followed by the same prox / Nesterov update as fista (:200-221), fixed step, per column.
+ * Needs float64 storage and d a multiple of 128. */
+typedef struct fos_gram fos_gram;
+int fos_gram_create(fos_design* h, fos_gram** out);
+int fos_gram_destroy(fos_gram* g);
+int fos_gram_info(const fos_gram* g, int* d, double* btb, float* build_ms, int* nsplit);
+int fos_gram_pointers(fos_gram* g, double** G_dev, double** c_dev);
+int fos_gram_download(fos_gram* g, double* G_out, double* c_out);
+int fos_gram_set_btb(fos_gram* g, double btb);
+/* X_out: n_lambda x d (row l = solution for alphas1[l]); obj_out: n_lambda objectives
+ * 0.5 x^T G x - c^T x + 0.5 b^T b (+0.5 alpha2 |x|^2) (+alpha1 |x|_1) of the final iterates. */
+int fos_gram_path_fista(fos_gram* g, const double* alphas1, int n_lambda, double alpha2, double step,
+                        int max_iter, double* X_out, double* obj_out, float* loop_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ generated in the dev container by ``tests/golden/make_golden.py`` (which
 imports /root/reference) and committed as ``tests/golden/*.npz``;
 ``tests/test_oracle_golden.py`` checks this restatement against every one.
 """
+from . import ref_numpy  # noqa: F401
 from .ref_numpy import (  # noqa: F401
     prox_l1,
     prox_elastic_net,

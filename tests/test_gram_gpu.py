@@ -1,0 +1,69 @@
+"""GPU: Gram-matrix mode (fp64 DMMA) and the batched multi-lambda path against numpy / the oracle."""
+import numpy as np
+import pytest
+
+import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def _design(n, d, seed):
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((n, d))
+    A = z.copy()
+    A[:, 1:] += 0.5 * z[:, :-1]
+    x_true = np.where(np.arange(d) % 9 == 0, 1.0, 0.0)
+    b = A @ x_true + 0.3 * rng.standard_normal(n)
+    return A, b
+
+
+@pytest.mark.parametrize("n,d", [(3000, 128), (5003, 256), (777, 384)])
+def test_gram_matches_numpy(n, d):
+    from fastoptsolver_b200.design import DeviceDesign
+    from fastoptsolver_b200.gram import GramDesign
+    A, b = _design(n, d, 1)
+    des = DeviceDesign.from_host(A, b)
+    gram = GramDesign(des)
+    G, c = gram.download()
+    G_ref = A.T @ A
+    assert harness.rel_err(G, G_ref) <= 1e-13
+    assert np.array_equal(G, G.T), "G must be exactly symmetric"
+    assert harness.rel_err(c, A.T @ b) <= 1e-13
+    assert abs(gram.btb - b @ b) <= 1e-13 * (b @ b)
+    # deterministic rebuild
+    G2, _ = GramDesign(des).download()
+    assert G2.tobytes() == G.tobytes()
+    des.close()
+
+
+def test_path_matches_reference_fista():
+    """Every column of the batched path == the reference fista for that penalty."""
+    import oracle
+    from fastoptsolver_b200 import gram as GM
+    A, b = _design(4000, 256, 2)
+    lam = float(np.max(np.abs(A.T @ b)))
+    alphas = 1.001 * lam * np.logspace(0, -3, 70)  # 70 penalties -> two column blocks, one padded
+    np.random.seed(0)
+    L = oracle.estimate_lipschitz(A)
+    for a2 in (0.0, 0.05 * lam):
+        X, info = GM.fista_path(A, b, alphas, alpha2=a2, max_iter=60, L=L + (a2 if a2 > 0 else 0.0))
+        for j in (0, 1, 17, 63, 64, 69):
+            # same L for both sides (estimate_lipschitz is pinned elsewhere)
+            x_ref, h = _oracle_fista_fixed_L(oracle, A, b, alphas[j], a2, L + (a2 if a2 > 0 else 0.0), 60)
+            assert harness.rel_err(X[j], x_ref) <= 1e-9 or np.linalg.norm(X[j] - x_ref) <= 1e-9 * np.linalg.norm(X[-1])
+            assert abs(info["obj"][j] - h[-1]) <= 1e-9 * abs(h[-1])
+            tie = 1e-6 * max(np.abs(x_ref).max(), 1e-300)
+            big = np.abs(x_ref) > tie
+            assert np.array_equal(np.sign(X[j][big]), np.sign(x_ref[big]))
+    assert np.all(X[0] == 0.0)                      # alpha1 > lambda_max -> zero solution
+
+
+def _oracle_fista_fixed_L(oracle, A, b, a1, a2, L, iters):
+    """oracle.fista with the Lipschitz estimate replaced by a given value."""
+    saved = oracle.ref_numpy.estimate_lipschitz
+    oracle.ref_numpy.estimate_lipschitz = lambda A_: L - (a2 if a2 > 0 else 0.0)
+    try:
+        x, h = oracle.fista(A, b, "elasticnet", a1, a2, max_iter=iters, return_history=True)
+    finally:
+        oracle.ref_numpy.estimate_lipschitz = saved
+    return x, h["obj"]
