@@ -57,6 +57,18 @@ class PGResult(C.Structure):
     ]
 
 
+class LbfgsParams(C.Structure):
+    _fields_ = [("m", C.c_int), ("max_iter", C.c_int), ("maxfun", C.c_int), ("maxls", C.c_int), ("obj_terms", C.c_int),
+                ("alpha1", C.c_double), ("alpha2", C.c_double), ("pgtol", C.c_double), ("factr", C.c_double),
+                ("x0", c_double_p)]
+
+
+class LbfgsResult(C.Structure):
+    _fields_ = [("x", c_double_p), ("obj_hist", c_double_p), ("f_final", C.c_double),
+                ("n_iters", C.c_int), ("n_fg", C.c_int), ("n_skipped", C.c_int), ("stop_reason", C.c_int),
+                ("loop_ms", C.c_float), ("kernel_launches", C.c_int64)]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks every one is exported
 SIGNATURES = {
     "fos_abi_version": (C.c_int, []),
@@ -87,6 +99,7 @@ SIGNATURES = {
     "fos_prox_elastic_net": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                        C.c_int]),
     "fos_prox_grad": (C.c_int, [C.c_void_p, C.POINTER(PGParams), C.POINTER(PGResult)]),
+    "fos_lbfgs": (C.c_int, [C.c_void_p, C.POINTER(LbfgsParams), C.POINTER(LbfgsResult)]),
     "fos_gram_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "fos_gram_destroy": (C.c_int, [C.c_void_p]),
     "fos_gram_info": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_float_p, c_int_p]),

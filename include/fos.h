@@ -182,6 +182,29 @@ typedef struct fos_pg_result {
 
 int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r);
 
+/* ---- device-resident L-BFGS ------------------------------------------------------------------
+ * The unconstrained path of L-BFGS-B as scipy.optimize.fmin_l_bfgs_b runs it for the reference
+ * (lbfgs.py:64-70: m = 10, factr = 1e7, pgtol = tol, maxfun = 15000, maxls = 20), with the
+ * (S, Y) history, the two-loop recursion and the More'-Thuente line search on the device.
+ * Minimises 0.5||Ax-b||^2 + 0.5 alpha2 ||x||^2 (the reference's `fg`, lbfgs.py:43-54: the L1 term
+ * is never in it); obj_hist records the full objective of every accepted iterate (the reference's
+ * callback, lbfgs.py:56-61; obj_terms as in fos_objective).  stop_reason: 1 ||g||_inf <= pgtol,
+ * 2 relative reduction <= factr*eps, 3 max_iter, 4 maxfun, 5 abnormal line-search termination. */
+typedef struct fos_lbfgs_params {
+    int m, max_iter, maxfun, maxls, obj_terms;
+    double alpha1, alpha2, pgtol, factr;
+    const double* x0; /* NULL = zeros (lbfgs.py:63) */
+} fos_lbfgs_params;
+typedef struct fos_lbfgs_result {
+    double* x;        /* d */
+    double* obj_hist; /* max_iter */
+    double f_final;   /* smooth loss at x (res[1] of fmin_l_bfgs_b, lbfgs.py:72) */
+    int n_iters, n_fg, n_skipped, stop_reason;
+    float loop_ms;
+    int64_t kernel_launches;
+} fos_lbfgs_result;
+int fos_lbfgs(fos_design* h, const fos_lbfgs_params* p, fos_lbfgs_result* r);
+
 /* ---- Gram-matrix mode (n >> d) and the batched regularisation path --------------------------
  * New capability (north_star item 4; no counterpart in the reference, which re-reads A every
  * iteration): G = A^T A, c = A^T b, b^T b are built once with fp64 tensor-core MMA, after

@@ -270,3 +270,51 @@ def test_sweep_driver_small():
     direct = [des.objective(x, 1, a1, 0.0) for x in log["x"][1:]]
     np.testing.assert_allclose(S.last_run["ista_obj"], direct, rtol=1e-12)
     des.close()
+
+
+def _lbfgs_pair(A, b, reg, a1, a2, **kw):
+    import oracle
+    from fastoptsolver_b200.lbfgs import LBFGSSolver
+    ref = oracle.LBFGSSolver(reg, a1, a2, **kw)
+    ref.fit(A, b)
+    dev = LBFGSSolver(reg, a1, a2, driver="device", **kw)
+    dev.fit(A, b)
+    return ref, dev
+
+
+def test_device_lbfgs_well_conditioned():
+    """Device L-BFGS (two-loop + More'-Thuente on the GPU) against scipy's L-BFGS-B driven by the
+    oracle: on a well-conditioned design the whole objective trace agrees."""
+    rng = np.random.default_rng(4)
+    n, d = 4000, 64
+    A = rng.standard_normal((n, d)) / np.sqrt(n)
+    A += 0.1 * rng.standard_normal((n, 1)) / np.sqrt(n)
+    x_true = rng.standard_normal(d)
+    b = A @ x_true + 0.01 * rng.standard_normal(n)
+    for reg, a1, a2 in (("ridge", 0.0, 0.05), ("elasticnet", 0.01, 0.05), ("lasso", 0.01, 0.0)):
+        ref, dev = _lbfgs_pair(A, b, reg, a1, a2, max_iter=100, tol=1e-9)
+        assert len(dev.history_) == len(ref.history_), (reg, len(dev.history_), len(ref.history_))
+        err = np.abs(np.array(dev.history_) - np.array(ref.history_)) / np.abs(ref.history_)
+        assert err.max() <= 1e-9, (reg, err.max())
+        assert abs(dev.final_obj_ - ref.final_obj_) <= 1e-10 * abs(ref.final_obj_)
+        assert harness.rel_err(dev.x_, ref.x_) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["mid", "wide", "c1"])
+def test_device_lbfgs_golden_designs(name):
+    """On the (ill-conditioned) golden designs: the first iterations match the reference's trace
+    and the converged objective agrees; in between the quasi-Newton recursion amplifies rounding."""
+    from fastoptsolver_b200.lbfgs import LBFGSSolver
+    A, b = cases.design(name)
+    g = harness.golden(name)
+    for key in ("lbfgs/ridge", "lbfgs/elasticnet"):
+        a1, a2 = (float(v) for v in g[f"{key}/alpha"])
+        spec = cases.solver_specs(name, A, b)[key]
+        dev = LBFGSSolver(spec["reg_type"], a1, a2, driver="device", **spec["kw"])
+        dev.fit(A, b)
+        ref_h = g[f"{key}/hobj"]
+        k = min(3, len(ref_h))
+        np.testing.assert_allclose(dev.history_[:k], ref_h[:k], rtol=1e-9)
+        assert abs(dev.history_[-1] - ref_h[-1]) <= 1e-7 * abs(ref_h[-1])
+        assert abs(len(dev.history_) - len(ref_h)) <= max(3, len(ref_h) // 4)
+        assert harness.rel_err(dev.x_, g[f"{key}/x"]) <= 1e-3

@@ -116,8 +116,11 @@ def test_dropin_modules_have_reference_names():
                                         "t_init_factor", "max_iter", "tol", "return_history"]
         assert list(inspect.signature(IS.estimate_lipschitz).parameters) == ["A", "n_iter", "tol"]
         LB = importlib.import_module("lbfgs")
-        assert list(inspect.signature(LB.LBFGSSolver.__init__).parameters) == [
-            "self", "reg_type", "alpha1", "alpha2", "max_iter", "tol", "eps"]
+        lb = inspect.signature(LB.LBFGSSolver.__init__).parameters
+        positional = [k for k, v in lb.items() if v.kind == v.POSITIONAL_OR_KEYWORD]
+        assert positional == ["self", "reg_type", "alpha1", "alpha2", "max_iter", "tol", "eps"]
+        # extras must be keyword-only so that reference call sites keep working
+        assert all(v.kind == v.KEYWORD_ONLY for k, v in lb.items() if k not in positional)
         assert LB.grad_call_times is IS.grad_call_times
         PO = importlib.import_module("prox_operators")
         assert list(inspect.signature(PO.prox_l1).parameters)[:2] == ["v", "tau"]
