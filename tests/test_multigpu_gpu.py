@@ -63,12 +63,36 @@ def _worker(rank, world, port, q):
                 ls_iters=base.ls_iters, grad_calls=base.grad_calls)
             out, spec = harness.run_case(be, name, key)
             harness.check_case(out, spec, name, key, 1e-10, lbfgs_trace_rtol=1e-7)
+            if key.startswith("lbfgs/"):
+                # device driver on the sharded design: same converged objective, identical on all ranks
+                g = harness.golden(name)
+                a1, a2 = (float(v) for v in g[f"{key}/alpha"])
+                dev = base.lbfgs_cls(spec["reg_type"], a1, a2, driver="device", **spec["kw"])
+                dev.fit(shard)
+                ref_h = g[f"{key}/hobj"]
+                np.testing.assert_allclose(dev.history_[:3], ref_h[:3], rtol=1e-9)
+                assert abs(dev.history_[-1] - ref_h[-1]) <= 1e-7 * abs(ref_h[-1])
+                out = {"x": dev.x_}
             # all ranks hold bit-identical iterates
             t = torch.from_numpy(np.asarray(out["x"]).copy()).cuda()
             lst = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(lst, t)
             assert all(torch.equal(lst[0], v) for v in lst), "ranks diverged"
             shard.close()
+        # Gram mode on row shards: local SYRK + one all-reduce of G == the single-matrix Gram
+        from fastoptsolver_b200.gram import GramDesign
+        rng = np.random.default_rng(1)
+        A = rng.standard_normal((2001, 128))
+        b = rng.standard_normal(2001)
+        lo, hi = multigpu.shard_bounds(2001, rank, world)
+        shard = multigpu.sharded_from_host(np.ascontiguousarray(A[lo:hi]), b[lo:hi], dist, device=rank)
+        gram = GramDesign(shard)
+        gram.allreduce(dist)
+        G, c = gram.download()
+        assert harness.rel_err(G, A.T @ A) <= 1e-13 and harness.rel_err(c, A.T @ b) <= 1e-13
+        assert abs(gram.btb - b @ b) <= 1e-12 * (b @ b)
+        gram.close()
+        shard.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
