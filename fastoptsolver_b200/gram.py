@@ -63,19 +63,15 @@ class GramDesign:
         return _CudaArray(g.value, (self.d, self.d)), _CudaArray(c.value, (self.d,))
 
     def allreduce(self, dist, group=None):
-        """Row-sharded ranks: sum G, c and b^T b over the ranks (the one bandwidth-relevant
-        collective of the whole path: d^2 doubles, once)."""
+        """Row-sharded ranks: sum the local Gram matrices over the ranks (the one
+        bandwidth-relevant collective of the whole path: d^2 doubles, once; a plain library
+        all-reduce).  c = A^T b and b^T b are already global: they come from a pass of the
+        streaming kernel, whose epilogue does the peer-memory exchange."""
         import torch
-        gd, cd = self.device_arrays()
+        gd, _ = self.device_arrays()
         G = torch.as_tensor(gd, device=f"cuda:{self.design.device}")
-        c = torch.as_tensor(cd, device=f"cuda:{self.design.device}")
         dist.all_reduce(G, group=group)
-        dist.all_reduce(c, group=group)
-        t = torch.tensor([self.btb], dtype=torch.float64, device=G.device)
-        dist.all_reduce(t, group=group)
         torch.cuda.synchronize(G.device)
-        self.btb = float(t.item())
-        _lib.check(_lib.load().fos_gram_set_btb(self._h, self.btb))
 
 
 class _CudaArray:
