@@ -86,6 +86,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_int64)]),
     "fos_design_download": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "fos_design_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fos_design_column_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_double_p]),
+    "fos_design_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "fos_design_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fos_time_grad_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "fos_design_lambda_max": (C.c_int, [C.c_void_p, c_double_p]),

@@ -8,6 +8,8 @@
 //   x_true = tile([5, 0, -0.02, -0.05, 1.5]);  b = A x_true + noise_std * N(0,1)
 // Randomness: Philox4x32-10 keyed by the seed, counter = (global row, group, draw), so any
 // row range of the virtual matrix can be produced independently (row-sharded ranks).
+#include <string.h>
+
 #include "fos_common.cuh"
 
 namespace {
@@ -135,6 +137,53 @@ __global__ void repack_cm_kernel(const T* __restrict__ src, T* __restrict__ dst,
     }
 }
 
+// ---------------------------------------------------------------- column statistics / z-scoring
+// part[cta][c] = sum over the CTA's row block of (A[i][c] - center[c])^p, p = 1 or 2.  Fixed
+// row partition and fixed-order final sum: deterministic.  One pass over A (HBM bound).
+template <typename T>
+__global__ void colstat_kernel(const T* __restrict__ A, long long n, int d, int lda, const double* __restrict__ center,
+                               int squared, double* __restrict__ part) {
+    const long long lo = (n * blockIdx.x) / gridDim.x, hi = (n * (blockIdx.x + 1LL)) / gridDim.x;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const double mu = center ? center[c] : 0.0;
+        double s0 = 0.0, s1 = 0.0;
+        long long r = lo;
+        for (; r + 1 < hi; r += 2) {
+            const double v0 = static_cast<double>(A[r * lda + c]) - mu;
+            const double v1 = static_cast<double>(A[(r + 1) * lda + c]) - mu;
+            s0 += squared ? v0 * v0 : v0;
+            s1 += squared ? v1 * v1 : v1;
+        }
+        if (r < hi) {
+            const double v0 = static_cast<double>(A[r * lda + c]) - mu;
+            s0 += squared ? v0 * v0 : v0;
+        }
+        part[static_cast<size_t>(blockIdx.x) * d + c] = s0 + s1;
+    }
+}
+
+__global__ void colstat_reduce_kernel(const double* __restrict__ part, int nparts, int d, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[static_cast<size_t>(p) * d + c];
+    out[c] = s;
+}
+
+// A[i][c] = (A[i][c] - shift[c]) / scale[c] in place (numpy: (A - mu) / sd)
+template <typename T>
+__global__ void affine_columns_kernel(T* __restrict__ A, long long n, int d, int lda, const double* __restrict__ shift,
+                                      const double* __restrict__ scale) {
+    const long long lo = (n * blockIdx.x) / gridDim.x, hi = (n * (blockIdx.x + 1LL)) / gridDim.x;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const double mu = shift[c], sd = scale[c];
+        for (long long r = lo; r < hi; ++r) {
+            const double v = static_cast<double>(A[r * lda + c]);
+            A[r * lda + c] = static_cast<T>(__ddiv_rn(__dsub_rn(v, mu), sd));
+        }
+    }
+}
+
 }  // namespace
 
 int fos_launch_synthetic(fos_design* h, unsigned long long seed, double noise, double rho1, double rho2,
@@ -165,4 +214,75 @@ int fos_launch_repack(const void* src_dev, void* dst_dev, long long rows, int d,
                                                        static_cast<float*>(dst_dev), rows, d, lda);
     FOS_CUDA(cudaGetLastError());
     return FOS_OK;
+}
+
+extern "C" int fos_design_column_sums(fos_design* h, const double* center, int squared, double* out, double* b_out) {
+    FOS_REQUIRE(h && out, "null pointer argument");
+    FOS_CUDA(cudaSetDevice(h->device));
+    const int d = h->d;
+    const int grid = h->sm_count * 4;
+    double *part = nullptr, *dout = nullptr, *dcen = nullptr;
+    auto cleanup = [&]() {
+        for (double* q : {part, dout, dcen})
+            if (q) cudaFree(q);
+    };
+    auto body = [&]() -> int {
+        const int dd = d + 1;  // last slot: the same statistic of b
+        FOS_CUDA(cudaMalloc(&part, static_cast<size_t>(grid) * dd * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&dout, dd * sizeof(double)));
+        if (center) {
+            FOS_CUDA(cudaMalloc(&dcen, dd * sizeof(double)));
+            FOS_CUDA(cudaMemcpyAsync(dcen, center, dd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        }
+        if (h->dtype == FOS_F64)
+            colstat_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(h->A), h->n, d, h->lda, dcen,
+                                                              squared, part);
+        else
+            colstat_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(h->A), h->n, d, h->lda, dcen,
+                                                             squared, part);
+        colstat_reduce_kernel<<<(d + 255) / 256, 256, 0, h->stream>>>(part, grid, d, dout);
+        // b as an n x 1 matrix
+        colstat_kernel<double><<<grid, 32, 0, h->stream>>>(h->b, h->n, 1, 1, dcen ? dcen + d : nullptr, squared,
+                                                          part + static_cast<size_t>(grid) * d);
+        colstat_reduce_kernel<<<1, 32, 0, h->stream>>>(part + static_cast<size_t>(grid) * d, grid, 1, dout + d);
+        FOS_CUDA(cudaGetLastError());
+        std::vector<double> host(dd);
+        FOS_CUDA(cudaMemcpyAsync(host.data(), dout, dd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(out, host.data(), d * sizeof(double));
+        if (b_out) *b_out = host[d];
+        return FOS_OK;
+    };
+    const int st = body();
+    cleanup();
+    return st;
+}
+
+extern "C" int fos_design_affine(fos_design* h, const double* shift, const double* scale, double b_shift) {
+    FOS_REQUIRE(h && shift && scale, "null pointer argument");
+    FOS_REQUIRE(h->owns_A, "cannot rewrite a borrowed matrix in place");
+    FOS_CUDA(cudaSetDevice(h->device));
+    const int d = h->d;
+    double* dv = nullptr;
+    FOS_CUDA(cudaMalloc(&dv, (2 * static_cast<size_t>(d) + 2) * sizeof(double)));
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaMemcpyAsync(dv, shift, d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FOS_CUDA(cudaMemcpyAsync(dv + d, scale, d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const double bs[2] = {b_shift, 1.0};
+        FOS_CUDA(cudaMemcpyAsync(dv + 2 * d, bs, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const int grid = h->sm_count * 4;
+        if (h->dtype == FOS_F64)
+            affine_columns_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<double*>(h->A), h->n, d, h->lda, dv,
+                                                                     dv + d);
+        else
+            affine_columns_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<float*>(h->A), h->n, d, h->lda, dv,
+                                                                    dv + d);
+        affine_columns_kernel<double><<<grid, 32, 0, h->stream>>>(h->b, h->n, 1, 1, dv + 2 * d, dv + 2 * d + 1);
+        FOS_CUDA(cudaGetLastError());
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        return FOS_OK;
+    };
+    const int st = body();
+    cudaFree(dv);
+    return st;
 }

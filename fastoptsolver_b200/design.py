@@ -108,6 +108,42 @@ class DeviceDesign:
         _lib.check(_lib.load().fos_design_download(self.handle, row0, rows, _ptr(A), _ptr(b)))
         return A, b
 
+    def column_sums(self, center=None, squared=False):
+        """Per-column sum (or centered sum of squares) over this rank's rows, plus the same for b."""
+        d = self.shape[1]
+        out = np.empty(d)
+        b_out = C.c_double()
+        cen = None if center is None else np.ascontiguousarray(center, dtype=np.float64)
+        _lib.check(_lib.load().fos_design_column_sums(self.handle, None if cen is None else _ptr(cen), int(squared),
+                                                      _ptr(out), C.byref(b_out)))
+        return out, b_out.value
+
+    def standardize(self, dist=None, group=None, n_total=None):
+        """z-score the columns of A and centre b in place on the device (two statistics passes +
+        one rewrite pass), like ``datagen.standardize`` on the host.  With ``dist`` the statistics
+        are summed over the row-sharded ranks.  Returns (mean, std, b_mean)."""
+        n = self.shape[0]
+
+        def allsum(vec):
+            if dist is None:
+                return vec
+            import torch
+            t = torch.from_numpy(np.ascontiguousarray(vec)).to(f"cuda:{self.device}")
+            dist.all_reduce(t, group=group)
+            return t.cpu().numpy()
+
+        n_all = float(allsum(np.array([float(n)]))[0]) if n_total is None else float(n_total)
+        s, bs = self.column_sums()
+        tot = allsum(np.concatenate([s, [bs]]))
+        mean = tot / n_all
+        sq, _ = self.column_sums(center=mean, squared=True)
+        sq = allsum(sq)
+        sd = np.sqrt(sq / n_all)
+        sd = np.where(sd > 0, sd, 1.0)
+        _lib.check(_lib.load().fos_design_affine(self.handle, _ptr(np.ascontiguousarray(mean[:-1])),
+                                                 _ptr(np.ascontiguousarray(sd)), float(mean[-1])))
+        return mean[:-1], sd, float(mean[-1])
+
     def lambda_max(self):
         out = C.c_double()
         _lib.check(_lib.load().fos_design_lambda_max(self.handle, C.byref(out)))

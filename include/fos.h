@@ -94,6 +94,13 @@ int fos_design_shape(const fos_design* h, int64_t* n, int64_t* d, int* dtype, in
 int fos_design_download(fos_design* h, int64_t row0, int64_t rows, void* A_out, double* b_out);
 /* device pointers of the resident arrays (for zero-copy wrappers) */
 int fos_design_pointers(fos_design* h, void** A_dev, double** b_dev);
+/* Column statistics of the resident design (one pass over A): out[c] = sum_i (A[i][c] - center[c])^p
+ * with p = 2 if `squared` else 1 (center may be NULL = 0; it has d+1 entries, the last for b);
+ * *b_out gets the same statistic of b.  Local rows only: sharded callers add the ranks' results. */
+int fos_design_column_sums(fos_design* h, const double* center, int squared, double* out, double* b_out);
+/* In place: A[i][c] = (A[i][c] - shift[c]) / scale[c], b[i] -= b_shift -- the z-scoring the reference's
+ * notebook applied to its data before calling the solvers. */
+int fos_design_affine(fos_design* h, const double* shift, const double* scale, double b_shift);
 /* enable/disable per-launch CUDA-event timing of the gradient kernel inside the solver loop */
 int fos_design_set_profile(fos_design* h, int enable);
 /* Diagnostic: average duration (CUDA events, solver stream) of `reps` back-to-back launches of

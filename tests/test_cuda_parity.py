@@ -318,3 +318,22 @@ def test_device_lbfgs_golden_designs(name):
         assert abs(dev.history_[-1] - ref_h[-1]) <= 1e-7 * abs(ref_h[-1])
         assert abs(len(dev.history_) - len(ref_h)) <= max(3, len(ref_h) // 4)
         assert harness.rel_err(dev.x_, g[f"{key}/x"]) <= 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_standardize(dtype):
+    """z-scoring on the device == datagen.standardize on the host (what the notebook did)."""
+    from fastoptsolver_b200 import datagen
+    from fastoptsolver_b200.design import DeviceDesign
+    A, b, _ = datagen.generate_correlated_design(3001, 35, seed=2)
+    A = A.astype(dtype)
+    des = DeviceDesign.from_host(A, b)
+    mu, sd, bm = des.standardize()
+    A_ref, b_ref = datagen.standardize(A.astype(np.float64), b)
+    A_dev, b_dev = des.download()
+    tol = 1e-12 if dtype == np.float64 else 2e-6
+    assert np.max(np.abs(A_dev - A_ref)) <= tol * max(1.0, np.abs(A_ref).max())
+    np.testing.assert_allclose(b_dev, b_ref, rtol=0, atol=1e-11 * np.abs(b).max())
+    np.testing.assert_allclose(mu, A.astype(np.float64).mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(sd, A.astype(np.float64).std(axis=0), rtol=1e-12)
+    des.close()
