@@ -136,9 +136,9 @@ __device__ __forceinline__ bool peer_exchange(const EpiArgs& e, Shared& sh, bool
     }
     __threadfence_system();
     cluster.sync();
-    if (leader) {
-        for (int p = 0; p < e.world; ++p) st_release_sys(e.peer.flag[p] + e.rank, epoch);
-    }
+    // one thread per peer publishes the arrival counter (the stores travel over NVLink in parallel)
+    if (cluster.block_rank() == 0 && threadIdx.x < e.world)
+        st_release_sys(e.peer.flag[threadIdx.x] + e.rank, epoch);
     if (threadIdx.x == 0) sh.sc[0] = 1.0;
     __syncthreads();
     if (threadIdx.x < e.world) {

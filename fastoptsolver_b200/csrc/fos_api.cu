@@ -3,6 +3,7 @@
 // passes and polls a pinned copy of the control block; every numerical decision is taken on
 // the device (epilogue_kernels.cu).
 #include <stdarg.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -125,6 +126,12 @@ static int design_alloc_work(fos_design* h) {
         FOS_CUDA(cudaMalloc(v, vb));
         FOS_CUDA(cudaMemsetAsync(*v, 0, vb, h->stream));
     }
+    // row partition of the streaming kernel: equal blocks to start with
+    h->row_lo_host.resize(h->n_parts + 1);
+    for (int c = 0; c <= h->n_parts; ++c) h->row_lo_host[c] = (h->n * c) / h->n_parts;
+    FOS_CUDA(cudaMalloc(&h->row_lo, (h->n_parts + 1) * sizeof(long long)));
+    FOS_CUDA(cudaMemcpyAsync(h->row_lo, h->row_lo_host.data(), (h->n_parts + 1) * sizeof(long long),
+                             cudaMemcpyHostToDevice, h->stream));
     FOS_CUDA(cudaMalloc(&h->ctrl, sizeof(FosCtrl)));
     FOS_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(FosCtrl), h->stream));
     FOS_CUDA(cudaMallocHost(&h->ctrl_host, 4 * sizeof(FosCtrl)));
@@ -134,13 +141,18 @@ static int design_alloc_work(fos_design* h) {
     return FOS_OK;
 }
 
+// Note on the row partition: equal contiguous blocks.  Per-CTA durations differ by up to 30 %
+// (tools/exp_cta_balance.py), but that is bandwidth arbitration, not lost throughput: when the
+// early CTAs retire the remaining ones absorb the freed HBM bandwidth, and re-weighting the blocks
+// to the measured per-CTA rates was measured to be slower (199 vs 209 it/s at 1M x 4096).
+
 static void design_free(fos_design* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->owns_A && h->A) cudaFree(h->A);
     if (h->owns_b && h->b) cudaFree(h->b);
-    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl};
+    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl, h->row_lo};
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -377,6 +389,35 @@ extern "C" int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms
     float ms = 0.f;
     FOS_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *ms_avg = ms / reps;
+    return FOS_OK;
+}
+
+// Debug: per-CTA start/end %globaltimer stamps of ONE gradient-kernel launch in `mode` (ns, relative
+// to the earliest start).  out has 2*n_parts entries; returns n_parts through *n_parts.
+extern "C" int fos_debug_cta_times(fos_design* h, int mode, long long* out, int cap, int* n_parts) {
+    FOS_REQUIRE(h && out && n_parts, "null pointer argument");
+    FOS_REQUIRE(cap >= 2 * h->n_parts, "output buffer too small");
+    FOS_CUDA(cudaSetDevice(h->device));
+    unsigned long long* buf = nullptr;
+    FOS_CUDA(cudaMalloc(&buf, 2 * static_cast<size_t>(h->n_parts) * sizeof(unsigned long long)));
+    FOS_CUDA(cudaMemset(buf, 0, 2 * static_cast<size_t>(h->n_parts) * sizeof(unsigned long long)));
+    FOS_TRY(fos_launch_grad(h, mode));  // warm-up without stamps
+    h->cta_times = buf;
+    int st = fos_launch_grad(h, mode);
+    h->cta_times = nullptr;
+    std::vector<unsigned long long> host(2 * h->n_parts);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(host.data(), buf, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (st != FOS_OK) return st;
+    if (e != cudaSuccess) {
+        fos_set_error("debug launch failed: %s", cudaGetErrorString(e));
+        return FOS_ERR_CUDA;
+    }
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < h->n_parts; ++i) t0 = std::min(t0, host[2 * i]);
+    for (size_t i = 0; i < host.size(); ++i) out[i] = static_cast<long long>(host[i] - t0);
+    *n_parts = h->n_parts;
     return FOS_OK;
 }
 

@@ -125,6 +125,8 @@ struct GradArgs {
     long long n;
     int d, lda, ldv;
     int mode_override;   // >= 0: use instead of ctrl->g_mode
+    const long long* row_lo;        // [n_parts + 1] row partition of the streaming kernel
+    unsigned long long* cta_times;  // debug: [n_parts][2] start/end %globaltimer per CTA (nullable)
 };
 
 // Everything the epilogue kernel needs.
@@ -179,6 +181,9 @@ struct fos_design {
     FosPeer peer{};
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
+    unsigned long long* cta_times = nullptr;  // debug buffer (fos_debug_cta_times)
+    long long* row_lo = nullptr;              // device: [n_parts + 1] row partition (streaming kernel)
+    std::vector<long long> row_lo_host;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
     // optional per-launch event timing of the gradient kernel
     bool profile = false;

@@ -108,6 +108,8 @@ int fos_design_set_profile(fos_design* h, int enable);
  * 2 = residual norm only, 8 = streaming probe (bulk-copy ring only, no arithmetic: the sustained
  * HBM read ceiling of this pipeline). */
 int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms_avg);
+/* Debug: per-CTA start/end timestamps (ns) of one gradient-kernel launch; out[2*n_parts]. */
+int fos_debug_cta_times(fos_design* h, int mode, long long* out, int cap, int* n_parts);
 /* lambda_max = ||A^T b||_inf (one fused pass), the usual scale for alpha1 */
 int fos_design_lambda_max(fos_design* h, double* out);
 
