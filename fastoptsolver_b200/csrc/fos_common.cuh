@@ -126,6 +126,7 @@ struct GradArgs {
     int d, lda, ldv;
     int mode_override;   // >= 0: use instead of ctrl->g_mode
     const long long* row_lo;        // [n_parts + 1] row partition of the streaming kernel
+    const int* sm_slot;             // [256] SM id -> partition slot (nullable: slot = blockIdx.x)
     unsigned long long* cta_times;  // debug: [n_parts][2] start/end %globaltimer per CTA (nullable)
 };
 
@@ -184,6 +185,8 @@ struct fos_design {
     unsigned long long* cta_times = nullptr;  // debug buffer (fos_debug_cta_times)
     long long* row_lo = nullptr;              // device: [n_parts + 1] row partition (streaming kernel)
     std::vector<long long> row_lo_host;
+    int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed
+    bool balanced = false;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
     // optional per-launch event timing of the gradient kernel
     bool profile = false;
@@ -197,7 +200,8 @@ cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cu
 int fos_launch_grad(fos_design* h, int mode_override);
 int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hist, double a1,
                         double a2, int bits);
-int fos_grad_plan(fos_design* h);  // picks kernel + n_parts, sets smem attributes
+int fos_grad_plan(fos_design* h);
+int fos_balance_rows(fos_design* h);  // SM-indexed row partition weighted by measured per-SM rates  // picks kernel + n_parts, sets smem attributes
 int fos_launch_prox(const double* v_dev, double* out_dev, long long len, double thresh,
                     double scale, cudaStream_t stream);
 int fos_launch_synthetic(fos_design* h, unsigned long long seed, double noise, double rho1,

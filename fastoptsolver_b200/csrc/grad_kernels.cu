@@ -114,12 +114,11 @@ struct StreamSmem {
 template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2>
 __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
                                                unsigned char* ring, int stage_bytes, int nstage,
-                                               long long lo, long long hi, bool use_b, uint64_t pol) {
+                                               long long lo, long long hi, bool use_b, uint64_t pol, int cta) {
     constexpr int VEC = Vec<T>::N;
     constexpr int NV = CPT / VEC;
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cta = blockIdx.x;
     const uint32_t row_bytes = static_cast<uint32_t>(a.lda) * sizeof(T);
     const int nst = static_cast<int>((hi - lo + R - 1) / R);
 
@@ -281,7 +280,12 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     if (tid == 0) {
         a.partial_s[2 * cta + 0] = s1;
         a.partial_s[2 * cta + 1] = s2;
-        if (a.cta_times) a.cta_times[2 * cta + 1] = fos_globaltimer();
+        if (a.cta_times) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            // end stamp in the low 48 bits, SM id above (debug only)
+            a.cta_times[2 * cta + 1] = (fos_globaltimer() & 0xFFFFFFFFFFFFull) | (static_cast<unsigned long long>(smid) << 48);
+        }
     }
 }
 
@@ -293,10 +297,19 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     __shared__ __align__(16) StreamSmem<NW, R> sm;
 
     const int tid = threadIdx.x;
-    const int cta = blockIdx.x, ncta = gridDim.x;
+    const int ncta = gridDim.x;
+    // Partition slot of this CTA.  With one persistent CTA per SM the slot can be tied to the SM
+    // the CTA landed on (the block scheduler's blockIdx -> SM map changes from launch to launch),
+    // which lets the row blocks be weighted by the SMs' measured streaming rates.
+    int cta = blockIdx.x;
+    if (a.sm_slot != nullptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        cta = a.sm_slot[smid & 255u];
+    }
 
-    // static contiguous row partition (equal blocks, table built once per design): deterministic
-    // summation order, bit-reproducible results.
+    // static contiguous row partition (table built once per design): deterministic summation
+    // order, bit-reproducible results for the lifetime of the design.
     const long long lo = a.row_lo[cta];
     const long long hi = a.row_lo[cta + 1];
     const int nst = static_cast<int>((hi - lo + R - 1) / R);
@@ -334,7 +347,7 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         return;
     }
     if (cta == 0 && tid == 0) a.ctrl->pass_t0 = fos_globaltimer();
-    if (a.cta_times && tid == 0) a.cta_times[2 * cta] = fos_globaltimer();
+    if (a.cta_times && tid == 0) a.cta_times[2 * cta] = fos_globaltimer() & 0xFFFFFFFFFFFFull;
 
     // ===== consumers =====
     if (mode & GM_PROBE) {
@@ -364,13 +377,13 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     const bool use_b = !(mode & GM_NOB);
     switch (mode & (GM_GRAD | GM_DOT2)) {
         case GM_GRAD:
-            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             break;
         case GM_DOT2:
-            stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             break;
         default:
-            stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol);
+            stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             break;
     }
 }
@@ -595,6 +608,7 @@ int fos_launch_grad(fos_design* h, int mode_override) {
     a.mode_override = mode_override;
     a.cta_times = h->cta_times;
     a.row_lo = h->row_lo;
+    a.sm_slot = (h->kern_kind == 1) ? h->sm_slot : nullptr;
     void* params[3];
     params[0] = &a;
     if (h->kern_kind == 1) {
