@@ -10,6 +10,7 @@ content fingerprint); pass a ``DeviceDesign`` in place of ``A`` to skip even tha
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 import zlib
 
@@ -192,37 +193,54 @@ _CACHE_MAX = 4
 
 
 def _fingerprint(A, b):
-    """Cheap content check: CRC of ~4k strided samples of A and of b plus the corners."""
+    """Content check for cache reuse: CRC of ~64k strided samples of A, of its first and last
+    rows, and of ALL of b.  (A full CRC of a 32 GB matrix would cost more than re-uploading it.)"""
     flat_n = A.shape[0] * A.shape[1]
-    step = max(1, flat_n // 4096)
-    rows = np.arange(0, flat_n, step) // A.shape[1]
-    cols = np.arange(0, flat_n, step) % A.shape[1]
-    crc = zlib.crc32(np.ascontiguousarray(A[rows, cols]).tobytes())
-    crc = zlib.crc32(np.ascontiguousarray(b[:: max(1, b.shape[0] // 4096)]).tobytes(), crc)
+    step = max(1, flat_n // 65536)
+    idx = np.arange(0, flat_n, step)
+    crc = zlib.crc32(np.ascontiguousarray(A[idx // A.shape[1], idx % A.shape[1]]).tobytes())
+    crc = zlib.crc32(np.ascontiguousarray(A[0]).tobytes(), crc)
     crc = zlib.crc32(np.ascontiguousarray(A[-1]).tobytes(), crc)
+    crc = zlib.crc32(np.ascontiguousarray(b).tobytes(), crc)
     return crc
 
 
 def as_design(A, b=None, device=0):
-    """Return a DeviceDesign for (A, b), uploading only when needed."""
+    """Return a DeviceDesign for (A, b), uploading only when needed.
+
+    A cached device copy is reused only for the *same array objects* (identity, still alive) with
+    unchanged shape/strides/dtype and matching content fingerprint.  The reference re-reads its
+    arrays on every call; if you mutate ``A`` in place between calls in a way the sampled
+    fingerprint cannot see, call ``clear_cache()`` (or set FOS_NO_CACHE=1 to upload every time)."""
     if isinstance(A, DeviceDesign):
         return A
     A = np.asarray(A)
     if b is None:
         raise ValueError("b is required when A is a host array")
     b = np.asarray(b)
+    if os.environ.get("FOS_NO_CACHE") == "1":
+        return DeviceDesign.from_host(A, b, device=device)
     key = (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str,
            b.__array_interface__["data"][0], b.shape, device)
     fp = _fingerprint(A, b.reshape(-1))
     hit = _CACHE.get(key)
-    if hit is not None and hit[1] == fp and hit[0]._h is not None:
+    if hit is not None and hit[1] == fp and hit[0]._h is not None and hit[2]() is _base_of(A):
         return hit[0]
     des = DeviceDesign.from_host(A, b, device=device)
     if len(_CACHE) >= _CACHE_MAX:
         old_key = next(iter(_CACHE))
         _CACHE.pop(old_key)      # freed by its finalizer once nobody else holds it
-    _CACHE[key] = (des, fp)
+    try:
+        ref = weakref.ref(_base_of(A))
+    except TypeError:            # not weak-referenceable: never reuse
+        ref = lambda: None       # noqa: E731
+    _CACHE[key] = (des, fp, ref)
     return des
+
+
+def _base_of(A):
+    """The object that owns A's memory (np.asarray of an ndarray returns the array itself)."""
+    return A
 
 
 def find_by_matrix(A, device=0):
@@ -232,13 +250,13 @@ def find_by_matrix(A, device=0):
         return A
     A = np.asarray(A)
     akey = (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str)
-    for key, (des, _) in _CACHE.items():
+    for key, (des, _, _r) in _CACHE.items():
         if key[:4] == akey and key[6] == device and des._h is not None:
             return des
     return None
 
 
 def clear_cache():
-    for des, _ in _CACHE.values():
+    for des, _, _r in _CACHE.values():
         des.close()
     _CACHE.clear()

@@ -337,3 +337,31 @@ def test_device_standardize(dtype):
     np.testing.assert_allclose(mu, A.astype(np.float64).mean(axis=0), rtol=1e-12)
     np.testing.assert_allclose(sd, A.astype(np.float64).std(axis=0), rtol=1e-12)
     des.close()
+
+
+def test_design_cache_semantics():
+    """numpy inputs are re-used only while they are the same, unchanged objects."""
+    from fastoptsolver_b200 import design as D
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((300, 24))
+    b = rng.standard_normal(300)
+    D.clear_cache()
+    d1 = D.as_design(A, b)
+    assert D.as_design(A, b) is d1                      # same objects, same content: reuse
+    b[5] += 1.0                                         # b is fully fingerprinted
+    d2 = D.as_design(A, b)
+    assert d2 is not d1
+    A[0, 3] = 7.0                                       # first / last rows are fingerprinted
+    d3 = D.as_design(A, b)
+    assert d3 is not d2
+    A2 = A.copy()                                       # equal content, different object: upload again
+    assert D.as_design(A2, b) is not d3
+    loss, g = d3.grad(np.ones(24))
+    import oracle
+    lr, gr = oracle.smooth_value_and_grad(np.ones(24), A, b)
+    assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
+    with pytest.raises(ValueError):
+        d3.grad(np.ones(5))
+    with pytest.raises(NotImplementedError):
+        D.DeviceDesign.from_host(np.zeros((4, 9000)), np.zeros(4))
+    D.clear_cache()
