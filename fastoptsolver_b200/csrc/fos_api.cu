@@ -81,7 +81,10 @@ static inline int elem_size(int dtype) { return dtype == FOS_F64 ? 8 : 4; }
 static int design_common_init(fos_design* h, long long n, long long d, int dtype, int device) {
     FOS_REQUIRE(n >= 1 && d >= 1, "design must have at least one row and one column (got %lld x %lld)", n, d);
     FOS_REQUIRE(dtype == FOS_F64 || dtype == FOS_F32, "dtype must be FOS_F64 or FOS_F32");
-    FOS_REQUIRE(d <= 8192, "d = %lld exceeds the supported maximum of 8192 columns", d);
+    if (d > 8192) {
+        fos_set_error("d = %lld exceeds the supported maximum of 8192 columns", d);
+        return FOS_ERR_UNSUPPORTED;
+    }
     int ndev = fos_device_count();
     if (ndev <= 0) {
         fos_set_error("no CUDA device visible: libfos_b200 has no CPU fallback");
@@ -684,7 +687,10 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
     FosHist none{};
     long long pairs = 0;
-    FOS_TRY(drive_passes(h, EOP_POWER, none, n_iter, [](const FosCtrl& s) { return s.g_mode == GM_SKIP; }, &pairs));
+    h->grad_only_hint = true;
+    const int pst = drive_passes(h, EOP_POWER, none, n_iter, [](const FosCtrl& s) { return s.g_mode == GM_SKIP; }, &pairs);
+    h->grad_only_hint = false;
+    FOS_TRY(pst);
     FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
     FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
     FOS_CUDA(cudaStreamSynchronize(h->stream));

@@ -182,6 +182,8 @@ struct fos_design {
     FosPeer peer{};
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
+    bool lite_ok = false;         // a gradient-only kernel variant exists for this shape
+    bool grad_only_hint = false;  // the running loop never asks for the second dot
     unsigned long long* cta_times = nullptr;  // debug buffer (fos_debug_cta_times)
     long long* row_lo = nullptr;              // device: [n_parts + 1] row partition (streaming kernel)
     std::vector<long long> row_lo_host;

@@ -289,7 +289,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     }
 }
 
-template <typename T, int NT, int CPT, int R>
+// LITE: gradient-only build (modes GM_GRAD [| GM_NOB]); used for wide rows (d > 4096) by the loops
+// that never need the second dot (L-BFGS, power iteration, fos_grad), where dropping v2 lets 256
+// threads own 32 columns each -- half the per-element reduction cost of the 512-thread build.
+template <typename T, int NT, int CPT, int R, bool LITE = false>
 __global__ void __launch_bounds__(NT, 1)
 grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     constexpr int NW = NT / 32;
@@ -375,6 +378,10 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         return;
     }
     const bool use_b = !(mode & GM_NOB);
+    if (LITE) {
+        stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
+        return;
+    }
     switch (mode & (GM_GRAD | GM_DOT2)) {
         case GM_GRAD:
             stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
@@ -524,9 +531,16 @@ struct StreamCfg {
     int nt, cpt, r;
 };
 
-template <typename T, int NT, int CPT, int R>
+template <typename T, int NT, int CPT, int R, bool LITE = false>
 StreamCfg make_cfg() {
-    return StreamCfg{reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R>), NT, CPT, R};
+    return StreamCfg{reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE>), NT, CPT, R};
+}
+
+// gradient-only variant for wide rows, if one exists
+bool pick_lite_cfg(int dtype, int lda, StreamCfg* out) {
+    if (lda <= 4096 || lda > 8192) return false;
+    *out = (dtype == FOS_F64) ? make_cfg<double, 256, 32, 1, true>() : make_cfg<float, 256, 32, 1, true>();
+    return true;
 }
 
 bool pick_stream_cfg(int dtype, int lda, StreamCfg* out) {
@@ -583,6 +597,11 @@ int fos_grad_plan(fos_design* h) {
         if (h->n < h->sm_count) h->n_parts = static_cast<int>(h->n > 0 ? h->n : 1);
         FOS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SMEM_RING_BUDGET));
+        StreamCfg lite;
+        const char* nl = getenv("FOS_NO_LITE");
+        h->lite_ok = pick_lite_cfg(h->dtype, h->lda, &lite) && !(nl && nl[0] == '1');
+        if (h->lite_ok)
+            FOS_CUDA(cudaFuncSetAttribute(lite.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RING_BUDGET));
     } else {
         h->kern_kind = 0;
         long long want = (h->n + GEN_WARPS * 16 - 1) / (GEN_WARPS * 16);
@@ -614,6 +633,9 @@ int fos_launch_grad(fos_design* h, int mode_override) {
     if (h->kern_kind == 1) {
         StreamCfg cfg;
         pick_stream_cfg(h->dtype, h->lda, &cfg);
+        const bool grad_only = (mode_override >= 0) ? ((mode_override & (GM_GRAD | GM_DOT2 | GM_PROBE)) == GM_GRAD)
+                                                    : h->grad_only_hint;
+        if (grad_only && h->lite_ok) pick_lite_cfg(h->dtype, h->lda, &cfg);
         const int elem = (h->dtype == FOS_F64) ? 8 : 4;
         int stage_bytes = cfg.r * h->lda * elem;
         stage_bytes = (stage_bytes + 127) & ~127;

@@ -634,7 +634,9 @@ extern "C" int fos_lbfgs(fos_design* h, const fos_lbfgs_params* p, fos_lbfgs_res
             }
             if (launched >= max_pairs) break;
             for (int i = 0; i < B && launched < max_pairs && status == FOS_OK; ++i, ++launched) {
+                h->grad_only_hint = true;
                 status = fos_launch_grad(h, -1);
+                h->grad_only_hint = false;
                 if (status == FOS_OK) {
                     cudaError_t le = fos_launch_ex(reinterpret_cast<const void*>(&lbfgs_epilogue_kernel),
                                                    dim3(FOS_EPI_CLUSTER), dim3(FOS_EPI_THREADS), 0, h->stream, params,

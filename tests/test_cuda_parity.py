@@ -365,3 +365,31 @@ def test_design_cache_semantics():
     with pytest.raises(NotImplementedError):
         D.DeviceDesign.from_host(np.zeros((4, 9000)), np.zeros(4))
     D.clear_cache()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("d", [4100, 8192])
+def test_wide_rows(d, dtype):
+    """4096 < d <= 8192: the 512-thread build (all modes) and the gradient-only 256x32 build."""
+    import oracle
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200.design import DeviceDesign
+    rng = np.random.default_rng(8)
+    n = 700
+    A = np.asarray(rng.standard_normal((n, d)) / np.sqrt(n), dtype=dtype)
+    b = rng.standard_normal(n)
+    A64 = A.astype(np.float64)
+    des = DeviceDesign.from_host(A, b)
+    x = rng.standard_normal(d)
+    loss, g = des.grad(x, 0.3)                                   # gradient-only kernel
+    lr, gr = oracle.smooth_value_and_grad(x, A64, b, 0.3)
+    assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
+    assert abs(des.objective(x, 3, 0.2, 0.3) - oracle.compute_objective(x, A64, b, "elasticnet", 0.2, 0.3)) <= 1e-12 * lr
+    a1 = 0.2 * float(np.max(np.abs(A64.T @ b)))
+    np.random.seed(0)
+    xr, hr = oracle.fista(A64, b, "lasso", a1, 0.0, max_iter=15, return_history=True)
+    np.random.seed(0)
+    xg, hg = S.fista(des, None, "lasso", a1, 0.0, max_iter=15, return_history=True)   # power iteration: lite; loop: full
+    assert harness.rel_err(xg, xr) <= 1e-10
+    np.testing.assert_allclose(hg["obj"], hr["obj"], rtol=1e-10)
+    des.close()
