@@ -190,10 +190,13 @@ def main():
             adaptive_restart=False, restart_threshold=1.0, want_history=True)
         return x, oh[:it], dict(S.last_run["solver"])
 
+    import torch
+
     def barrier():
         if dist is not None:
             dist.barrier()
-        # the solver stream is synchronised inside fos_prox_grad before it returns
+        # fos_prox_grad synchronises its own stream before returning; this covers torch's streams
+        torch.cuda.synchronize(device)
 
     solve(W, False)                                   # warm-up steps (untimed)
     barrier()
