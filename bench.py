@@ -292,6 +292,8 @@ def main():
         }
     if rank == 0:
         print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
     des.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -73,3 +73,11 @@ def sharded_synthetic(n_total, d, dist, group=None, device=None, dtype=np.float6
     des = DeviceDesign.synthetic(hi - lo, d, dtype, row0=lo, device=device, **scenario)
     attach(des, dist, group)
     return des
+
+
+def close(des: DeviceDesign, dist, group=None):
+    """Free a sharded design.  The exchange window of a rank is read by its peers' epilogue
+    kernels, so every rank must be done with its last solve before any window goes away:
+    barrier first, then close."""
+    dist.barrier(group)
+    des.close()
