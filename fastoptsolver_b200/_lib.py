@@ -57,6 +57,16 @@ class PGResult(C.Structure):
     ]
 
 
+class PathParams(C.Structure):
+    _fields_ = [("alphas1", c_double_p), ("n_lambda", C.c_int), ("alpha2", C.c_double), ("step", C.c_double),
+                ("max_iter", C.c_int), ("tol", C.c_double), ("check_every", C.c_int), ("X0", c_double_p)]
+
+
+class PathResult(C.Structure):
+    _fields_ = [("X", c_double_p), ("obj", c_double_p), ("n_iters", C.c_int), ("last_max_step", C.c_double),
+                ("tile_rows", C.c_int), ("loop_ms", C.c_float), ("kernel_launches", C.c_int64)]
+
+
 class LbfgsParams(C.Structure):
     _fields_ = [("m", C.c_int), ("max_iter", C.c_int), ("maxfun", C.c_int), ("maxls", C.c_int), ("obj_terms", C.c_int),
                 ("alpha1", C.c_double), ("alpha2", C.c_double), ("pgtol", C.c_double), ("factr", C.c_double),
@@ -109,8 +119,7 @@ SIGNATURES = {
     "fos_gram_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "fos_gram_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fos_gram_set_btb": (C.c_int, [C.c_void_p, C.c_double]),
-    "fos_gram_path_fista": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
-                                      C.c_void_p, c_float_p, C.POINTER(C.c_int64)]),
+    "fos_gram_path_fista": (C.c_int, [C.c_void_p, C.POINTER(PathParams), C.POINTER(PathResult)]),
 }
 
 _lib = None

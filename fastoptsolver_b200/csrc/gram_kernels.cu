@@ -148,9 +148,10 @@ __global__ void gram_reduce_kernel(const double* __restrict__ W, double* __restr
 }
 
 // ------------------------------------------------------------------------------------------
-// batched path iteration: out tile 128 (i) x 64 (l), K chunks of 16
+// batched path iteration: out tile PM (i) x 64 (l), K chunks of 16.  PM = 128 when there are
+// enough penalties to fill the SMs, 64 / 32 for short penalty lists (more, smaller tiles).
 // ------------------------------------------------------------------------------------------
-constexpr int PM = 128, PN = 64, PK = 16, PLD = PK + 4, PSTAGES = 4;
+constexpr int PN = 64, PK = 16, PLD = PK + 4, PSTAGES = 4;
 
 struct PathArgs {
     const double* G;      // [d][d] row-major, symmetric
@@ -162,11 +163,19 @@ struct PathArgs {
     double alpha2, tau, beta;
     int d, Lpad;
     int mode;             // 0: FISTA step, 1: objective partials of X (Yin = X)
-    double* obj_part;     // [d/128][Lpad][4]: x^T G x, c^T x, |x|_1, |x|^2 partials per i-block
+    double* obj_part;     // [d/PM][Lpad][4]: x^T G x, c^T x, |x|_1, |x|^2 partials per i-block
+    double* step_part;    // [d/PM][Lpad]: sum_i (x+ - x)^2 partials (nullable: not a check iteration)
 };
 
+template <int PM>
 __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
+    constexpr int WI = PM / 32;          // warps along i
+    constexpr int WL = 8 / WI;           // warps along l
+    constexpr int LW = PN / WL;          // l columns per warp
+    constexpr int NJ = LW / 8;           // mma blocks along l per warp
+    constexpr int CH = (PM + PN) * 8 / 256;  // 16-byte chunks per thread and stage
     extern __shared__ __align__(16) double smem[];  // [PSTAGES][(PM+PN)][PLD]
+    __shared__ double part[8][LW][4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int i0 = blockIdx.x * PM, l0 = blockIdx.y * PN;
     const int nst = p.d / PK;
@@ -176,8 +185,8 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
             double* base = smem + static_cast<size_t>(st % PSTAGES) * ((PM + PN) * PLD);
             const int k0 = st * PK;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int chunk = tid + 256 * q;  // (128 + 64) rows x 8 chunks = 1536
+            for (int q = 0; q < CH; ++q) {
+                const int chunk = tid + 256 * q;
                 const int row = chunk >> 3, c16 = chunk & 7;
                 const double* src = (row < PM) ? p.G + static_cast<size_t>(i0 + row) * p.d + k0 + c16 * 2
                                                : p.Yin + static_cast<size_t>(l0 + row - PM) * p.d + k0 + c16 * 2;
@@ -187,12 +196,12 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
         cp_async_commit();
     };
 
-    double acc[4][4][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int wi = warp >> 1, wl = warp & 1;  // 4 x 2 warps, warp tile 32 (i) x 32 (l)
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wi = warp / WL, wl = warp % WL;  // warp tile 32 (i) x LW (l)
     const int fk = lane & 3, fc = lane >> 2;
 
 #pragma unroll
@@ -205,29 +214,38 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
         const double* tY = tG + PM * PLD;
 #pragma unroll
         for (int k4 = 0; k4 < PK; k4 += 4) {
-            double a[4], b[4];
+            double a[4], b[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = tG[(wi * 32 + i * 8 + fc) * PLD + k4 + fk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = tY[(wl * 32 + j * 8 + fc) * PLD + k4 + fk];
+            for (int j = 0; j < NJ; ++j) b[j] = tY[(wl * LW + j * 8 + fc) * PLD + k4 + fk];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
+
+    // per-(l) sums of this thread: [0..3] objective pieces (mode 1) or [0] squared step (mode 0)
+    double sums[NJ][2][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sums[j][e][q] = 0.0;
 
     if (p.mode == 0) {
         // fused FISTA update on the tile (same roundings as the single-lambda epilogue)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int col = i0 + wi * 32 + i * 8 + fc;
-                    const int l = l0 + wl * 32 + j * 8 + fk * 2 + e;
+                    const int l = l0 + wl * LW + j * 8 + fk * 2 + e;
                     const size_t idx = static_cast<size_t>(l) * p.d + col;
                     const double y = p.Yin[idx], xk = p.X[idx];
                     double g = __dsub_rn(acc[i][j][e], p.c[col]);
@@ -237,51 +255,49 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
                     if (a1 > 0.0) v = fos_soft_threshold(v, __dmul_rn(p.tau, a1));
                     p.X[idx] = v;
                     p.Yout[idx] = __dadd_rn(v, __dmul_rn(p.beta, __dsub_rn(v, xk)));
+                    const double dx = v - xk;
+                    sums[j][e][0] = fma(dx, dx, sums[j][e][0]);
                 }
+        if (p.step_part == nullptr) return;
     } else {
-        // objective partials over this CTA's 128 columns: per l, sum_i x_i (Gx)_i etc.
-        __shared__ double part[8][32][4];  // [warp][l within warp tile][4 sums]
-        double sums[4][2][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) sums[j][e][q] = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int col = i0 + wi * 32 + i * 8 + fc;
-                    const int l = l0 + wl * 32 + j * 8 + fk * 2 + e;
+                    const int l = l0 + wl * LW + j * 8 + fk * 2 + e;
                     const double x = p.Yin[static_cast<size_t>(l) * p.d + col];
                     sums[j][e][0] = fma(x, acc[i][j][e], sums[j][e][0]);
                     sums[j][e][1] = fma(x, p.c[col], sums[j][e][1]);
                     sums[j][e][2] += fabs(x);
                     sums[j][e][3] = fma(x, x, sums[j][e][3]);
                 }
-        // reduce over the 8 lanes that share fk (lane>>2 varies): xor 4, 8, 16
+    }
+    // reduce over the 8 lanes that share fk (lane>>2 varies): xor 4, 8, 16
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    double v = sums[j][e][q];
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    if (fc == 0) part[warp][j * 8 + fk * 2 + e][q] = v;
-                }
-        __syncthreads();
-        // combine the 4 i-warps of each l half, fixed order; 64 l x 4 sums = 256 threads
-        const int l_loc = tid >> 2, q = tid & 3;
-        const int wl2 = l_loc >> 5, lw = l_loc & 31;
-        double t = 0.0;
+            for (int q = 0; q < 4; ++q) {
+                double v = sums[j][e][q];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (fc == 0) part[warp][j * 8 + fk * 2 + e][q] = v;
+            }
+    __syncthreads();
+    // combine the WI i-warps of each l, fixed order; 64 l x 4 sums = 256 threads
+    const int l_loc = tid >> 2, q = tid & 3;
+    const int wl2 = l_loc / LW, lw = l_loc % LW;
+    double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) t += part[w * 2 + wl2][lw][q];
+    for (int w = 0; w < WI; ++w) t += part[w * WL + wl2][lw][q];
+    if (p.mode == 0) {
+        if (q == 0) p.step_part[static_cast<size_t>(blockIdx.x) * p.Lpad + l0 + l_loc] = t;
+    } else {
         p.obj_part[(static_cast<size_t>(blockIdx.x) * p.Lpad + l0 + l_loc) * 4 + q] = t;
     }
 }
@@ -298,6 +314,25 @@ __global__ void path_obj_finish_kernel(const double* __restrict__ part, int nblk
     if (alpha2 > 0.0) v += 0.5 * alpha2 * s[3];
     if (alpha1[l] > 0.0) v += alpha1[l] * s[2];
     obj[l] = v;
+}
+
+// max over the real columns of ||x+ - x||_2, from the per-i-block partials (fixed order)
+__global__ void path_step_finish_kernel(const double* __restrict__ part, int nblk, int Lpad, int n_lambda,
+                                        double* __restrict__ out) {
+    __shared__ double red[256];
+    double m = 0.0;
+    for (int l = threadIdx.x; l < n_lambda; l += blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += part[static_cast<size_t>(b) * Lpad + l];
+        m = fmax(m, sqrt(s));
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 }  // namespace
@@ -444,49 +479,84 @@ extern "C" int fos_gram_set_btb(fos_gram* g, double btb) {
     return FOS_OK;
 }
 
-extern "C" int fos_gram_path_fista(fos_gram* g, const double* alphas1, int n_lambda, double alpha2, double step,
-                                   int max_iter, double* X_out, double* obj_out, float* loop_ms, int64_t* launches) {
-    FOS_REQUIRE(g && alphas1 && n_lambda >= 1 && max_iter >= 0 && step > 0.0, "bad argument");
+template <int PM>
+static cudaError_t launch_path(const PathArgs& p, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(PSTAGES) * (PM + PN) * PLD * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    path_step_kernel<PM><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_path_pm(int pm, const PathArgs& p, cudaStream_t st) {
+    if (pm == 128) return launch_path<128>(p, st);
+    if (pm == 64) return launch_path<64>(p, st);
+    return launch_path<32>(p, st);
+}
+
+extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_path_result* pr) {
+    FOS_REQUIRE(g && pp && pr && pp->alphas1, "null pointer argument");
+    FOS_REQUIRE(pp->n_lambda >= 1 && pp->max_iter >= 0 && pp->step > 0.0, "bad argument");
+    FOS_REQUIRE(pp->check_every >= 1 || pp->tol <= 0.0, "check_every must be >= 1 when tol > 0");
     FOS_CUDA(cudaSetDevice(g->device));
-    const int d = g->d;
+    const int d = g->d, n_lambda = pp->n_lambda;
     const int Lpad = (n_lambda + PN - 1) / PN * PN;
+    // i-tile: the largest that still gives every SM a tile
+    int pm = 128;
+    while (pm > 32 && static_cast<long long>(d / pm) * (Lpad / PN) < 120) pm /= 2;
+    const int nblk = d / pm;
     const size_t mat = static_cast<size_t>(Lpad) * d;
-    double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr;
+    double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr,
+           *spart = nullptr, *smax = nullptr;
+    double* smax_host = nullptr;
     auto cleanup = [&]() {
-        for (double* q : {Y0, Y1, X, a1, part, obj})
+        for (double* q : {Y0, Y1, X, a1, part, obj, spart, smax})
             if (q) cudaFree(q);
+        if (smax_host) cudaFreeHost(smax_host);
     };
     auto body = [&]() -> int {
         FOS_CUDA(cudaMalloc(&Y0, mat * sizeof(double)));
         FOS_CUDA(cudaMalloc(&Y1, mat * sizeof(double)));
         FOS_CUDA(cudaMalloc(&X, mat * sizeof(double)));
         FOS_CUDA(cudaMalloc(&a1, Lpad * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&part, static_cast<size_t>(d / PM) * Lpad * 4 * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&part, static_cast<size_t>(nblk) * Lpad * 4 * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&spart, static_cast<size_t>(nblk) * Lpad * sizeof(double)));
         FOS_CUDA(cudaMalloc(&obj, Lpad * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&smax, sizeof(double)));
+        FOS_CUDA(cudaMallocHost(&smax_host, sizeof(double)));
         FOS_CUDA(cudaMemsetAsync(Y0, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(Y1, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(X, 0, mat * sizeof(double), g->stream));
+        if (pp->X0) {  // warm start: x_0 = y_0 = X0 (rows beyond n_lambda stay zero)
+            FOS_CUDA(cudaMemcpyAsync(X, pp->X0, static_cast<size_t>(n_lambda) * d * sizeof(double),
+                                     cudaMemcpyHostToDevice, g->stream));
+            FOS_CUDA(cudaMemcpyAsync(Y0, X, static_cast<size_t>(n_lambda) * d * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, g->stream));
+        }
         std::vector<double> al(Lpad, 0.0);
-        for (int l = 0; l < n_lambda; ++l) al[l] = alphas1[l];
+        for (int l = 0; l < n_lambda; ++l) al[l] = pp->alphas1[l];
         FOS_CUDA(cudaMemcpyAsync(a1, al.data(), Lpad * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-        const size_t smem = static_cast<size_t>(PSTAGES) * (PM + PN) * PLD * sizeof(double);
-        FOS_CUDA(cudaFuncSetAttribute(path_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
         PathArgs p{};
         p.G = g->G;
         p.c = g->c;
         p.X = X;
         p.alpha1 = a1;
-        p.alpha2 = alpha2;
-        p.tau = step;
+        p.alpha2 = pp->alpha2;
+        p.tau = pp->step;
         p.d = d;
         p.Lpad = Lpad;
         p.obj_part = part;
-        const dim3 grid(d / PM, Lpad / PN);
         double t_prev = 1.0;
         int64_t n_launch = 0;
+        int iters = 0;
+        double last_step = -1.0;
         FOS_CUDA(cudaEventRecord(g->ev0, g->stream));
-        for (int k = 0; k < max_iter; ++k) {
+        for (int k = 0; k < pp->max_iter; ++k) {
             // Nesterov momentum of fista (iterative_solvers.py:219-221), same for every column
             const double t_cur = 0.5 * (1.0 + sqrt(1.0 + 4.0 * (t_prev * t_prev)));
             p.beta = (t_prev - 1.0) / t_cur;
@@ -494,24 +564,40 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const double* alphas1, int n_lam
             p.mode = 0;
             p.Yin = (k & 1) ? Y1 : Y0;
             p.Yout = (k & 1) ? Y0 : Y1;
-            path_step_kernel<<<grid, dim3(256), smem, g->stream>>>(p);
+            const bool check = pp->tol > 0.0 && ((k + 1) % pp->check_every == 0);
+            p.step_part = check ? spart : nullptr;
+            FOS_CUDA(launch_path_pm(pm, p, g->stream));
             ++n_launch;
+            ++iters;
+            if (check) {
+                // stop when every column's step ||x_{k+1}-x_k||_2 is below tol (iterative_solvers.py:238)
+                path_step_finish_kernel<<<1, 256, 0, g->stream>>>(spart, nblk, Lpad, n_lambda, smax);
+                FOS_CUDA(cudaMemcpyAsync(smax_host, smax, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+                FOS_CUDA(cudaStreamSynchronize(g->stream));
+                ++n_launch;
+                last_step = *smax_host;
+                if (last_step < pp->tol) break;
+            }
         }
         FOS_CUDA(cudaEventRecord(g->ev1, g->stream));
         p.mode = 1;
         p.Yin = X;
         p.Yout = nullptr;
-        path_step_kernel<<<grid, dim3(256), smem, g->stream>>>(p);
-        path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, d / PM, Lpad, a1, alpha2,
+        p.step_part = nullptr;
+        FOS_CUDA(launch_path_pm(pm, p, g->stream));
+        path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, nblk, Lpad, a1, pp->alpha2,
                                                                                    0.5 * g->bb, obj);
         n_launch += 2;
         FOS_CUDA(cudaGetLastError());
         FOS_CUDA(cudaStreamSynchronize(g->stream));
-        if (X_out)
-            FOS_CUDA(cudaMemcpy(X_out, X, static_cast<size_t>(n_lambda) * d * sizeof(double), cudaMemcpyDeviceToHost));
-        if (obj_out) FOS_CUDA(cudaMemcpy(obj_out, obj, n_lambda * sizeof(double), cudaMemcpyDeviceToHost));
-        if (loop_ms) FOS_CUDA(cudaEventElapsedTime(loop_ms, g->ev0, g->ev1));
-        if (launches) *launches = n_launch;
+        if (pr->X)
+            FOS_CUDA(cudaMemcpy(pr->X, X, static_cast<size_t>(n_lambda) * d * sizeof(double), cudaMemcpyDeviceToHost));
+        if (pr->obj) FOS_CUDA(cudaMemcpy(pr->obj, obj, n_lambda * sizeof(double), cudaMemcpyDeviceToHost));
+        FOS_CUDA(cudaEventElapsedTime(&pr->loop_ms, g->ev0, g->ev1));
+        pr->kernel_launches = n_launch;
+        pr->n_iters = iters;
+        pr->last_max_step = last_step;
+        pr->tile_rows = pm;
         return FOS_OK;
     };
     const int st = body();

@@ -80,12 +80,16 @@ class _CudaArray:
                                          "version": 3, "strides": None}
 
 
-def fista_path(A, b, alphas1, alpha2=0.0, t_init_factor=1.0, max_iter=500, L=None, gram=None):
+def fista_path(A, b, alphas1, alpha2=0.0, t_init_factor=1.0, max_iter=500, L=None, gram=None, tol=0.0,
+               check_every=10, X0=None):
     """FISTA for every alpha1 in ``alphas1`` at once (fixed step, no restart).
 
     Returns (X, info): X has one row per penalty; info holds the objectives of the final
     iterates, the Lipschitz estimate and timings.  ``L`` defaults to the reference's estimate
-    (``estimate_lipschitz``: power iteration started from numpy's global RNG) + alpha2."""
+    (``estimate_lipschitz``: power iteration started from numpy's global RNG) + alpha2.
+    ``tol`` > 0 stops once every column's step norm ||x_{k+1}-x_k|| is below it (the step-norm
+    rule of fista, iterative_solvers.py:238, tested every ``check_every`` iterations); ``X0``
+    (one row per penalty) warm-starts the columns, e.g. from a neighbouring path."""
     des = as_design(A, b)
     own = gram is None
     if own:
@@ -97,13 +101,18 @@ def fista_path(A, b, alphas1, alpha2=0.0, t_init_factor=1.0, max_iter=500, L=Non
             L += alpha2
     X = np.empty((alphas1.size, gram.d))
     obj = np.empty(alphas1.size)
-    ms = C.c_float()
-    launches = C.c_int64()
-    _lib.check(_lib.load().fos_gram_path_fista(
-        gram.handle, C.c_void_p(alphas1.ctypes.data), alphas1.size, float(alpha2), float(t_init_factor / L),
-        int(max_iter), C.c_void_p(X.ctypes.data), C.c_void_p(obj.ctypes.data), C.byref(ms), C.byref(launches)))
-    info = {"obj": obj, "L": float(L), "loop_ms": ms.value, "build_ms": gram.build_ms, "launches": launches.value,
-            "nsplit": gram.nsplit}
+    p = _lib.PathParams(alphas1=alphas1.ctypes.data_as(_lib.c_double_p), n_lambda=alphas1.size, alpha2=float(alpha2),
+                        step=float(t_init_factor / L), max_iter=int(max_iter), tol=float(tol),
+                        check_every=int(check_every))
+    if X0 is not None:
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        if X0.shape != X.shape:
+            raise ValueError(f"X0 must have shape {X.shape}, got {X0.shape}")
+        p.X0 = X0.ctypes.data_as(_lib.c_double_p)
+    r = _lib.PathResult(X=X.ctypes.data_as(_lib.c_double_p), obj=obj.ctypes.data_as(_lib.c_double_p))
+    _lib.check(_lib.load().fos_gram_path_fista(gram.handle, C.byref(p), C.byref(r)))
+    info = {"obj": obj, "L": float(L), "loop_ms": r.loop_ms, "build_ms": gram.build_ms, "launches": r.kernel_launches,
+            "nsplit": gram.nsplit, "iters": r.n_iters, "last_max_step": r.last_max_step, "tile_rows": r.tile_rows}
     if own:
         gram.close()
     return X, info

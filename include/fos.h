@@ -228,10 +228,26 @@ int fos_gram_info(const fos_gram* g, int* d, double* btb, float* build_ms, int* 
 int fos_gram_pointers(fos_gram* g, double** G_dev, double** c_dev);
 int fos_gram_download(fos_gram* g, double* G_out, double* c_out);
 int fos_gram_set_btb(fos_gram* g, double btb);
-/* X_out: n_lambda x d (row l = solution for alphas1[l]); obj_out: n_lambda objectives
- * 0.5 x^T G x - c^T x + 0.5 b^T b (+0.5 alpha2 |x|^2) (+alpha1 |x|_1) of the final iterates. */
-int fos_gram_path_fista(fos_gram* g, const double* alphas1, int n_lambda, double alpha2, double step,
-                        int max_iter, double* X_out, double* obj_out, float* loop_ms, int64_t* launches);
+typedef struct fos_path_params {
+    const double* alphas1; /* n_lambda L1 weights */
+    int n_lambda;
+    double alpha2;         /* shared L2 weight (smooth part) */
+    double step;           /* t_init_factor / L, shared by all columns */
+    int max_iter;
+    double tol;            /* > 0: stop once every column's step norm is below tol (iterative_solvers.py:238) */
+    int check_every;       /* evaluate the stop test every this many iterations */
+    const double* X0;      /* n_lambda x d warm start, NULL = zeros (iterative_solvers.py:150) */
+} fos_path_params;
+typedef struct fos_path_result {
+    double* X;   /* n_lambda x d: row l = solution for alphas1[l] */
+    double* obj; /* n_lambda: 0.5 x^T G x - c^T x + 0.5 b^T b (+0.5 alpha2 |x|^2) (+alpha1 |x|_1) */
+    int n_iters;
+    double last_max_step;
+    int tile_rows;
+    float loop_ms;
+    int64_t kernel_launches;
+} fos_path_result;
+int fos_gram_path_fista(fos_gram* g, const fos_path_params* p, fos_path_result* r);
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,45 @@ def _oracle_fista_fixed_L(oracle, A, b, a1, a2, L, iters):
     finally:
         oracle.ref_numpy.estimate_lipschitz = saved
     return x, h["obj"]
+
+
+def test_path_small_lists_tolerance_and_warm_start():
+    """Short penalty lists use the 32-row tile; tol stops early; a warm start from the solution
+    stops at the first check."""
+    import oracle
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    A, b = _design(3000, 256, 5)
+    lam = float(np.max(np.abs(A.T @ b)))
+    alphas = lam * np.array([0.5, 0.2, 0.05])
+    np.random.seed(0)
+    L = oracle.estimate_lipschitz(A)
+    des = DeviceDesign.from_host(A, b)
+    gram = GM.GramDesign(des)
+    X, info = GM.fista_path(des, None, alphas, max_iter=40, L=L, gram=gram)
+    assert info["tile_rows"] == 32 and info["iters"] == 40
+    for j, a1 in enumerate(alphas):
+        x_ref, h = _oracle_fista_fixed_L(oracle, A, b, a1, 0.0, L, 40)
+        assert harness.rel_err(X[j], x_ref) <= 1e-9
+        assert abs(info["obj"][j] - h[-1]) <= 1e-9 * abs(h[-1])
+    # tolerance stop: the reference stops when ||x_{k+1}-x_k|| < tol; the batch stops when all columns do
+    Xt, it = GM.fista_path(des, None, alphas, max_iter=5000, L=L, gram=gram, tol=1e-7, check_every=5)
+    assert it["iters"] < 5000 and it["iters"] % 5 == 0 and 0 <= it["last_max_step"] < 1e-7
+    iters_ref = []
+    for a1 in alphas:
+        saved = oracle.ref_numpy.estimate_lipschitz
+        oracle.ref_numpy.estimate_lipschitz = lambda A_: L
+        try:
+            _, h = oracle.fista(A, b, "lasso", a1, 0.0, max_iter=5000, tol=1e-7, return_history=True)
+        finally:
+            oracle.ref_numpy.estimate_lipschitz = saved
+        iters_ref.append(len(h["obj"]))
+    # (FISTA step norms are not monotone and the batch needs every column below tol at a check,
+    # so it may run a few checks past the slowest column's first crossing)
+    assert max(iters_ref) <= it["iters"] <= max(iters_ref) + 25
+    # warm start from the converged path: first check already passes
+    Xw, iw = GM.fista_path(des, None, alphas, max_iter=5000, L=L, gram=gram, tol=1e-6, check_every=5, X0=Xt)
+    assert iw["iters"] == 5
+    assert harness.rel_err(Xw, Xt) <= 1e-6
+    gram.close()
+    des.close()
