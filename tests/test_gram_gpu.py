@@ -109,3 +109,23 @@ def test_path_small_lists_tolerance_and_warm_start():
     assert harness.rel_err(Xw, Xt) <= 1e-6
     gram.close()
     des.close()
+
+
+def test_warm_started_path_matches_cold_batch():
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    import oracle
+    A, b = _design(3000, 256, 6)
+    lam = float(np.max(np.abs(A.T @ b)))
+    alphas = lam * np.logspace(-0.3, -2, 24)
+    np.random.seed(0)
+    L = oracle.estimate_lipschitz(A)
+    des = DeviceDesign.from_host(A, b)
+    gram = GM.GramDesign(des)
+    Xc, ic = GM.fista_path(des, None, alphas, max_iter=20000, L=L, gram=gram, tol=1e-9, check_every=10)
+    Xw, iw = GM.fista_path_warm(des, None, alphas, chunk=8, tol=1e-9, L=L, gram=gram)
+    assert harness.rel_err(Xw, Xc) <= 1e-6
+    np.testing.assert_allclose(iw["obj"], ic["obj"], rtol=1e-10)
+    assert sum(iw["iters"]) > 0 and len(iw["iters"]) == 3
+    gram.close()
+    des.close()
