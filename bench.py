@@ -321,11 +321,15 @@ def e2e_run(des, alpha1, K, n, d, dist, local_rank):
         dist.barrier()
     np.random.seed(0)
     t0 = time.perf_counter()
+    upload_s = None
     if dist is not None:
         shard = multigpu.sharded_from_host(A_h, b_h, dist, device=local_rank)
+        upload_s = time.perf_counter() - t0
         x, hist = S.fista(shard, None, "lasso", alpha1, 0.0, max_iter=K, return_history=True)
     else:
         shard = None
+        D.as_design(A_h, b_h, device=local_rank)      # the upload fista() would do itself, timed apart
+        upload_s = time.perf_counter() - t0
         x, hist = S.fista(A_h, b_h, "lasso", alpha1, 0.0, max_iter=K, return_history=True)
     wall = time.perf_counter() - t0
     if dist is not None:
@@ -339,7 +343,8 @@ def e2e_run(des, alpha1, K, n, d, dist, local_rank):
     h2d = rows * d * 8 + rows * 8
     d2h = (K + 1) * d * 8 + K * 8
     return {"value": K / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-            "wall_s": wall, "loop_ms": info["loop_ms"], "lipschitz_ms": lip["gpu_ms"],
+            "wall_s": wall, "upload_s": upload_s, "h2d_GBps": (h2d / upload_s / 1e9) if upload_s else None,
+            "loop_ms": info["loop_ms"], "lipschitz_ms": lip["gpu_ms"],
             "lipschitz_iters": lip["iters"], "bytes_are": "per rank",
             "what": "fista(A, b, 'lasso', a1, 0, max_iter=K, return_history=True) on pinned host numpy "
                     "arrays (each rank its row block): upload of A+b, power iteration, K iterations, "
