@@ -393,3 +393,41 @@ def test_wide_rows(d, dtype):
     assert harness.rel_err(xg, xr) <= 1e-10
     np.testing.assert_allclose(hg["obj"], hr["obj"], rtol=1e-10)
     des.close()
+
+
+def test_full_size_properties_1Mx4096():
+    """BASELINE config 3 at full size (1M x 4096 fp64, 32.8 GB): properties that need no oracle.
+    The design equals the concatenation of two independently generated row shards (Philox is
+    keyed by the global row), so gradient and loss must be the shard sums; plus linearity,
+    determinism, fused loss == objective pass, and a short FISTA run whose recorded objective
+    equals the objective of its iterates."""
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200.design import DeviceDesign
+    n, d = 1_000_000, 4096
+    sc = dict(seed=3, noise_std=1.0, rho1=0.8, rho2=0.9)
+    full = DeviceDesign.synthetic(n, d, **sc)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(d) * (rng.random(d) < 0.1)
+    loss, g = full.grad(x, 0.0)
+    assert full.grad(x, 0.0)[1].tobytes() == g.tobytes()
+    assert abs(full.objective(x, 0, 0.0, 0.0) - loss) <= 1e-12 * loss
+    lo = DeviceDesign.synthetic(n // 2, d, row0=0, **sc)
+    hi = DeviceDesign.synthetic(n - n // 2, d, row0=n // 2, **sc)
+    l1, g1 = lo.grad(x, 0.0)
+    l2, g2 = hi.grad(x, 0.0)
+    assert abs((l1 + l2) - loss) <= 1e-12 * loss
+    assert harness.rel_err(g1 + g2, g) <= 1e-12
+    lo.close()
+    hi.close()
+    y = rng.standard_normal(d)
+    g0 = full.grad(np.zeros(d))[1]
+    lhs = full.grad(x + y)[1] - g0
+    rhs = (g - g0) + (full.grad(y)[1] - g0)
+    assert harness.rel_err(lhs, rhs) <= 1e-12
+    a1 = 0.1 * full.lambda_max()
+    np.random.seed(0)
+    xk, h = S.fista(full, None, "lasso", a1, 0.0, max_iter=4, return_history=True)
+    for xi, oi in zip(h["x"][1:], h["obj"]):
+        assert abs(full.objective(xi, 1, a1, 0.0) - oi) <= 1e-12 * abs(oi)
+    assert h["obj"][-1] < h["obj"][0]
+    full.close()
