@@ -130,9 +130,9 @@ def host_threads():
 def pick_sample_rows(n, d, requested):
     if requested:
         return min(n, requested)
-    # ~0.5 GB of A: 500 passes (200 for the Lipschitz estimate + 3 per iteration) stay
-    # within a few tens of seconds on the box's host cores
-    return int(min(n, max(1024, (512 << 20) // (8 * d))))
+    # ~2 GB of A: 260 passes (200 for the Lipschitz estimate + 3 per iteration x 20) are
+    # 10-20 s of work for the box's host cores
+    return int(min(n, max(1024, (2 << 30) // (8 * d))))
 
 
 # ------------------------------------------------------------------------------- main
