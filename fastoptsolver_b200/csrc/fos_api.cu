@@ -142,8 +142,8 @@ static int design_alloc_work(fos_design* h) {
     memset(h->ctrl_host, 0, 4 * sizeof(FosCtrl));
     FOS_CUDA(cudaStreamSynchronize(h->stream));
     {
-        // opt-in (see the note above fos_balance_rows): it shortens an isolated pass by ~9 % but
-        // measured slightly slower in sustained loops, which are power-capped
+        // FOS_BALANCE=1 forces the rate-weighted partition on; by default it is switched on when
+        // the design joins >= 4 ranks (fos_comm_attach), where the GPUs are not power-capped
         const char* e = getenv("FOS_BALANCE");
         if (e && e[0] == '1') FOS_TRY(fos_balance_rows(h));
     }
@@ -165,8 +165,10 @@ static int design_alloc_work(fos_design* h) {
 // Measured (1M x 4096 fp64, B200): an isolated pass drops from 4.93 to 4.49 ms and the CTA finish
 // spread from 30 % to 4 %, but 100 back-to-back FISTA steps run at 199 it/s instead of 203-209
 // (1 GPU) and 386 instead of 392 (2 GPUs): the sustained loop sits at the 1 kW power cap, where
-// keeping every SM busy to the end buys nothing.  Hence opt-in: FOS_BALANCE=1.  The default is
-// equal blocks indexed by blockIdx (bit-reproducible across processes and GPUs).
+// keeping every SM busy to the end buys nothing.  With the rows spread over 8 GPUs each GPU draws
+// ~380 W, is not capped, and the weighted partition wins: 1520 vs 1443 it/s (kernel 0.592 vs
+// 0.640 ms).  Policy: on when a design joins >= 4 ranks, off otherwise; FOS_BALANCE=1/0 forces it.
+// Without it the blocks are equal and indexed by blockIdx (bit-reproducible across processes).
 #include <map>
 #include <mutex>
 static std::mutex g_bal_mutex;
@@ -194,7 +196,7 @@ int fos_balance_rows(fos_design* h) {
     // slot table: identity (SM ids are 0..sm_count-1)
     std::vector<int> slot(256, 0);
     for (int i = 0; i < 256; ++i) slot[i] = (i < P) ? i : (i % P);
-    FOS_CUDA(cudaMalloc(&h->sm_slot, 256 * sizeof(int)));
+    if (h->sm_slot == nullptr) FOS_CUDA(cudaMalloc(&h->sm_slot, 256 * sizeof(int)));
     FOS_CUDA(cudaMemcpy(h->sm_slot, slot.data(), 256 * sizeof(int), cudaMemcpyHostToDevice));
 
     std::lock_guard<std::mutex> lock(g_bal_mutex);
@@ -958,6 +960,10 @@ extern "C" int fos_comm_attach(fos_design* h, const void* ipc_handles, int world
         h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
     }
     h->world = world;
+    {
+        const char* e = getenv("FOS_BALANCE");
+        if (world >= 4 && !(e && e[0] == '0') && !h->balanced) FOS_TRY(fos_balance_rows(h));
+    }
     return FOS_OK;
 }
 
