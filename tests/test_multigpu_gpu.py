@@ -79,6 +79,27 @@ def _worker(rank, world, port, q):
             dist.all_gather(lst, t)
             assert all(torch.equal(lst[0], v) for v in lst), "ranks diverged"
             shard.close()
+        # A shard large enough for the streaming kernel (and, from 4 ranks on, the rate-weighted
+        # SM-indexed row blocks): the sharded solve equals the single-GPU solve of the same design
+        from fastoptsolver_b200 import iterative_solvers as S
+        from fastoptsolver_b200.design import DeviceDesign
+        n_tot, d_big = world * 40000, 1024
+        sc = dict(seed=9, noise_std=0.5, rho1=0.5, rho2=0.7)
+        shard = multigpu.sharded_synthetic(n_tot, d_big, dist, device=rank, **sc)
+        full = DeviceDesign.synthetic(n_tot, d_big, device=rank, **sc)
+        lam = full.lambda_max()
+        assert abs(shard.lambda_max() - lam) <= 1e-12 * lam
+        for kw in (dict(), dict(backtracking=True, t_init_factor=2.0)):
+            np.random.seed(0)
+            xs, hs = S.fista(shard, None, "lasso", 0.1 * lam, 0.0, max_iter=30, return_history=True, **kw)
+            ls_s = list(S.ls_call_iters)
+            np.random.seed(0)
+            xf, hf = S.fista(full, None, "lasso", 0.1 * lam, 0.0, max_iter=30, return_history=True, **kw)
+            assert harness.rel_err(xs, xf) <= 1e-10
+            np.testing.assert_allclose(hs["obj"], hf["obj"], rtol=1e-10)
+            assert ls_s == list(S.ls_call_iters)
+        multigpu.close(shard, dist)
+        full.close()
         # Gram mode on row shards: local SYRK + one all-reduce of G == the single-matrix Gram
         from fastoptsolver_b200.gram import GramDesign
         rng = np.random.default_rng(1)
