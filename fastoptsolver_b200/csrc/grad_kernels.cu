@@ -172,25 +172,30 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 }
         }
 
-        // per-thread partial dots: two independent chains per dot
+        // per-thread partial dots: NCH independent FMA chains per dot (fixed assignment of
+        // elements to chains and a fixed combine order: deterministic)
+        constexpr int NCH = (CPT >= 16) ? 4 : 2;
         double d1[R], d2[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            double p1a = 0.0, p1b = 0.0, p2a = 0.0, p2b = 0.0;
+            double p1[NCH], p2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) p1[c] = p2[c] = 0.0;
 #pragma unroll
             for (int j = 0; j < NV; ++j)
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    if (((j * VEC + e) & 1) == 0) {
-                        if (GRAD) p1a = fma(av[r][j][e], v1[j][e], p1a);
-                        if (DOT2) p2a = fma(av[r][j][e], v2[j][e], p2a);
-                    } else {
-                        if (GRAD) p1b = fma(av[r][j][e], v1[j][e], p1b);
-                        if (DOT2) p2b = fma(av[r][j][e], v2[j][e], p2b);
-                    }
+                    const int c = (j * VEC + e) % NCH;
+                    if (GRAD) p1[c] = fma(av[r][j][e], v1[j][e], p1[c]);
+                    if (DOT2) p2[c] = fma(av[r][j][e], v2[j][e], p2[c]);
                 }
-            d1[r] = GRAD ? p1a + p1b : 0.0;
-            d2[r] = DOT2 ? p2a + p2b : 0.0;
+            if (NCH == 4) {
+                d1[r] = GRAD ? (p1[0] + p1[1]) + (p1[2] + p1[3]) : 0.0;
+                d2[r] = DOT2 ? (p2[0] + p2[1]) + (p2[2] + p2[3]) : 0.0;
+            } else {
+                d1[r] = GRAD ? p1[0] + p1[1] : 0.0;
+                d2[r] = DOT2 ? p2[0] + p2[1] : 0.0;
+            }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
