@@ -96,6 +96,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_int64)]),
     "fos_design_download": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "fos_design_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fos_design_upload_gram": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_float_p, c_float_p]),
+    "fos_design_upload_gram_set": (C.c_int, [C.c_void_p, C.c_int]),
     "fos_design_column_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_double_p]),
     "fos_design_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "fos_design_set_profile": (C.c_int, [C.c_void_p, C.c_int]),

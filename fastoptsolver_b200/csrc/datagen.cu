@@ -262,6 +262,7 @@ extern "C" int fos_design_affine(fos_design* h, const double* shift, const doubl
     FOS_REQUIRE(h && shift && scale, "null pointer argument");
     FOS_REQUIRE(h->owns_A, "cannot rewrite a borrowed matrix in place");
     FOS_CUDA(cudaSetDevice(h->device));
+    fos_upload_gram_drop(h);  // A changes: a Gram matrix accumulated under the upload is stale
     const int d = h->d;
     double* dv = nullptr;
     FOS_CUDA(cudaMalloc(&dv, (2 * static_cast<size_t>(d) + 2) * sizeof(double)));

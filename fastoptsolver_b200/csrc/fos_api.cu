@@ -269,6 +269,7 @@ static void design_free(fos_design* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->owns_A && h->A) cudaFree(h->A);
     if (h->owns_b && h->b) cudaFree(h->b);
+    fos_upload_gram_drop(h);
     void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl, h->row_lo, h->sm_slot};
     for (void* p : bufs)
         if (p) cudaFree(p);
@@ -308,6 +309,55 @@ static int alloc_matrix(fos_design* h) {
     return FOS_OK;
 }
 
+// Chunked H2D copy of a dense float64 C-order matrix with the Gram accumulation of the arrived
+// rows running underneath on a second stream.  Copy stream: h->stream.
+static int upload_with_gram(fos_design* h, const void* A) {
+    cudaStream_t cs = nullptr;
+    FOS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evs;
+    cudaEvent_t t_done = nullptr;
+    auto body = [&]() -> int {
+        FOS_TRY(fos_upload_gram_begin(h, cs));
+        const long long chunk = fos_upload_gram_chunk_rows(h);
+        const size_t row_bytes = static_cast<size_t>(h->d) * sizeof(double);
+        FOS_CUDA(cudaEventCreate(&t_done));
+        FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+        for (long long r0 = 0; r0 < h->n; r0 += chunk) {
+            const long long rows = std::min<long long>(chunk, h->n - r0);
+            FOS_CUDA(cudaMemcpyAsync(static_cast<char*>(h->A) + static_cast<size_t>(r0) * row_bytes,
+                                     static_cast<const char*>(A) + static_cast<size_t>(r0) * row_bytes,
+                                     static_cast<size_t>(rows) * row_bytes, cudaMemcpyHostToDevice, h->stream));
+            if (h->up_W) {
+                cudaEvent_t e;
+                FOS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                evs.push_back(e);
+                FOS_CUDA(cudaEventRecord(e, h->stream));
+                FOS_CUDA(cudaStreamWaitEvent(cs, e, 0));
+                FOS_TRY(fos_upload_gram_chunk(h, r0, rows, cs));
+            }
+        }
+        FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+        FOS_CUDA(cudaStreamWaitEvent(cs, h->ev1, 0));
+        FOS_TRY(fos_upload_gram_finish(h, cs));  // reduces the splits, synchronises cs
+        FOS_CUDA(cudaEventRecord(t_done, cs));
+        FOS_CUDA(cudaStreamSynchronize(cs));
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        FOS_CUDA(cudaEventElapsedTime(&h->up_copy_ms, h->ev0, h->ev1));
+        FOS_CUDA(cudaEventElapsedTime(&h->up_tail_ms, h->ev1, t_done));
+        return FOS_OK;
+    };
+    const int st = body();
+    if (st != FOS_OK) {
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(h->stream);
+        fos_upload_gram_drop(h);
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (t_done) cudaEventDestroy(t_done);
+    cudaStreamDestroy(cs);
+    return st;
+}
+
 extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
                                  int64_t row_stride, int64_t col_stride, int device, fos_design** out) {
     FOS_REQUIRE(A && b && out, "null pointer argument");
@@ -319,7 +369,12 @@ extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int6
         FOS_CUDA(cudaMemcpyAsync(h->b, b, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         if (col_stride == 1 && row_stride >= d) {
             // C order (possibly with a row pitch): strided copy straight into the padded layout
-            if (h->lda == d && row_stride == d) {
+            if (h->lda == d && row_stride == d && fos_upload_gram_eligible(h)) {
+                // dense float64, tall: copy in row chunks and push every chunk that has arrived
+                // through the SYRK kernel on a second stream -- G = A^T A is ready a few ms after
+                // the last byte (gram_kernels.cu), and estimate_lipschitz then iterates on G
+                FOS_TRY(upload_with_gram(h, A));
+            } else if (h->lda == d && row_stride == d) {
                 // dense on both sides: one linear copy (full PCIe rate from pinned memory)
                 FOS_CUDA(cudaMemcpyAsync(h->A, A, static_cast<size_t>(n) * d * es, cudaMemcpyHostToDevice, h->stream));
             } else {
@@ -416,6 +471,28 @@ extern "C" int fos_design_shape(const fos_design* h, int64_t* n, int64_t* d, int
     if (d) *d = h->d;
     if (dtype) *dtype = h->dtype;
     if (lda) *lda = h->lda;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_upload_gram(fos_design* h, double** G_dev, int* state, float* copy_ms, float* tail_ms) {
+    FOS_REQUIRE(h, "null design");
+    if (G_dev) *G_dev = h->G_up;
+    if (state) *state = h->G_up ? h->G_state : 0;
+    if (copy_ms) *copy_ms = h->up_copy_ms;
+    if (tail_ms) *tail_ms = h->up_tail_ms;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_upload_gram_set(fos_design* h, int state) {
+    FOS_REQUIRE(h, "null design");
+    FOS_REQUIRE(state == 0 || state == 2, "state must be 0 (discard) or 2 (summed over all ranks)");
+    if (state == 0) {
+        FOS_CUDA(cudaSetDevice(h->device));
+        fos_upload_gram_drop(h);
+    } else {
+        FOS_REQUIRE(h->G_up != nullptr, "this design holds no Gram matrix");
+        h->G_state = 2;
+    }
     return FOS_OK;
 }
 
@@ -682,6 +759,10 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     FOS_REQUIRE(h && v0 && L_out, "null pointer argument");
     FOS_REQUIRE(n_iter >= 1, "n_iter must be >= 1");
     FOS_CUDA(cudaSetDevice(h->device));
+    // a Gram matrix accumulated under the upload (summed over the ranks if the rows are sharded):
+    // iterate on it instead of streaming A twice a hundred times
+    if (h->G_up && ((h->world == 1 && h->G_state == 1) || (h->world > 1 && h->G_state == 2)))
+        return fos_gram_power_iter(h, v0, n_iter, tol, L_out, iters_out, gpu_ms_out);
     FosCtrl* c = h->ctrl_host;
     memset(c, 0, sizeof(FosCtrl));
     c->g_mode = GM_GRAD | GM_NOB;

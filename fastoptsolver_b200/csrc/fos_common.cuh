@@ -190,6 +190,12 @@ struct fos_design {
     int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed
     bool balanced = false;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
+    // Gram matrix of the local rows accumulated under the host->device upload (gram_kernels.cu)
+    double* G_up = nullptr;   // [d][d], owned
+    int G_state = 0;          // 0 none, 1 local rows, 2 summed over all ranks by the caller
+    double* up_W = nullptr;   // split workspace, alive only during the upload
+    int up_nsplit = 0;
+    float up_copy_ms = 0.f, up_tail_ms = 0.f;  // upload duration / Gram work left after the last byte arrived
     // optional per-launch event timing of the gradient kernel
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
@@ -208,6 +214,15 @@ int fos_launch_prox(const double* v_dev, double* out_dev, long long len, double 
                     double scale, cudaStream_t stream);
 int fos_launch_synthetic(fos_design* h, unsigned long long seed, double noise, double rho1,
                          double rho2, long long row0);
+// upload-overlapped Gram accumulation and the power iteration on it (gram_kernels.cu)
+bool fos_upload_gram_eligible(const fos_design* h);
+long long fos_upload_gram_chunk_rows(const fos_design* h);
+int fos_upload_gram_begin(fos_design* h, cudaStream_t s);
+int fos_upload_gram_chunk(fos_design* h, long long row0, long long rows, cudaStream_t s);
+int fos_upload_gram_finish(fos_design* h, cudaStream_t s);
+void fos_upload_gram_drop(fos_design* h);
+int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out, int* iters_out,
+                        float* gpu_ms_out);
 int fos_launch_repack(const void* src_dev, void* dst_dev, long long rows, int d, int lda,
                       long long row_stride, long long col_stride, int dtype, cudaStream_t s);
 

@@ -14,6 +14,8 @@
 // row pitch is padded by 4 doubles, which makes every DMMA fragment load conflict free.
 // Bound: the fp64 tensor pipe (n d^2 FMA for the build, d^2 Lambda per path iteration).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -51,6 +53,7 @@ struct SyrkArgs {
     long long rows_per_split;  // multiple of GKB
     double* W;               // [nsplit][dpad][dpad]
     long long dpad;
+    int accumulate;          // 1: W[split] += tile (row chunks arriving one after the other)
 };
 
 __global__ void __launch_bounds__(256, 1) gram_syrk_kernel(const SyrkArgs g) {
@@ -126,7 +129,14 @@ __global__ void __launch_bounds__(256, 1) gram_syrk_kernel(const SyrkArgs g) {
         for (int j = 0; j < 8; ++j) {
             const long long row = static_cast<long long>(bi) * GT + wi * 32 + i * 8 + fc;
             const long long col = static_cast<long long>(bj) * GT + wj * 64 + j * 8 + fk * 2;
-            *reinterpret_cast<double2*>(out + row * g.dpad + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            double2* dst = reinterpret_cast<double2*>(out + row * g.dpad + col);
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (g.accumulate) {  // this (tile, split) slot belongs to this CTA alone; chunks are stream ordered
+                const double2 old = *dst;
+                v.x += old.x;
+                v.y += old.y;
+            }
+            *dst = v;
         }
 }
 
@@ -335,6 +345,63 @@ __global__ void path_step_finish_kernel(const double* __restrict__ part, int nbl
     if (threadIdx.x == 0) out[0] = red[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// power iteration on the Gram matrix: w = G v; L = ||w||; v = w / L  (estimate_lipschitz,
+// iterative_solvers.py:45-60, with A^T(A v) replaced by (A^T A) v).  Two launches per step,
+// all of them queued up front; after the stop test fires the remaining ones return at once.
+// ------------------------------------------------------------------------------------------
+struct GramPowerState {
+    double L, L_prev, tol;
+    int pit, pit_max, done, pad;
+};
+
+__global__ void __launch_bounds__(256) gram_matvec_kernel(const double* __restrict__ G, const double* __restrict__ v,
+                                                          double* __restrict__ w, int d, const GramPowerState* st) {
+    if (st->done) return;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d) return;
+    const double2* g2 = reinterpret_cast<const double2*>(G + static_cast<size_t>(row) * d);
+    const double2* v2 = reinterpret_cast<const double2*>(v);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const int n2 = d / 2;  // d is a multiple of 128: n2 is a multiple of 64
+    for (int c = lane; c < n2; c += 64) {
+        const double2 a0 = g2[c], a1 = g2[c + 32];
+        const double2 x0 = v2[c], x1 = v2[c + 32];
+        s[0] = fma(a0.x, x0.x, s[0]);
+        s[1] = fma(a0.y, x0.y, s[1]);
+        s[2] = fma(a1.x, x1.x, s[2]);
+        s[3] = fma(a1.y, x1.y, s[3]);
+    }
+    const double t = fos_warp_sum((s[0] + s[1]) + (s[2] + s[3]));
+    if (lane == 0) w[row] = t;
+}
+
+__global__ void __launch_bounds__(1024) gram_power_finish_kernel(const double* __restrict__ w, double* __restrict__ v,
+                                                                 int d, GramPowerState* st) {
+    if (st->done) return;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double s = 0.0;
+    for (int c = tid; c < d; c += 1024) s = fma(w[c], w[c], s);
+    s = fos_warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        const double t = fos_warp_sum(red[lane]);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    const double L = sqrt(red[0]);
+    for (int c = tid; c < d; c += 1024) v[c] = __ddiv_rn(w[c], L);
+    if (tid == 0) {
+        const int pit = st->pit + 1;
+        st->done = (fabs(L - st->L_prev) < st->tol) || (pit >= st->pit_max);
+        st->L = L;
+        st->L_prev = L;
+        st->pit = pit;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -364,6 +431,156 @@ static void gram_free(fos_gram* g) {
     delete g;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Gram matrix accumulated under the host->device upload (fos_design_create), and the power
+// iteration on it.  While the PCIe copy of a dense float64 design is in flight the SMs are
+// idle; the rows that have already arrived are pushed through the SYRK kernel chunk by chunk
+// (d^2 FMA per row against 8 d bytes over PCIe: hidden for d <= 4096), so that
+// estimate_lipschitz (iterative_solvers.py:45-60: <= 100 x two passes over A in the reference)
+// costs <= 100 products with the d x d matrix once the upload ends.
+// ------------------------------------------------------------------------------------------
+static size_t syrk_smem_bytes() { return static_cast<size_t>(GSTAGES) * 2 * GKB * GLD * sizeof(double); }
+
+static int syrk_pick_split(const fos_design* h, int ntiles, long long rows_avail, long long d) {
+    int best = 1;
+    double best_eff = 0.0;
+    long long max_split = std::min<long long>(h->sm_count, rows_avail / (4 * GKB));
+    max_split = std::min<long long>(max_split, (1536LL << 20) / (d * d * 8));  // workspace <= 1.5 GB
+    max_split = std::max<long long>(1, ntiles >= 64 ? std::min<long long>(max_split, 16) : max_split);
+    for (int s = 1; s <= max_split; ++s) {
+        const long long units = static_cast<long long>(ntiles) * s;
+        const long long waves = (units + h->sm_count - 1) / h->sm_count;
+        const double eff = static_cast<double>(units) / (waves * h->sm_count);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = s;
+        }
+    }
+    return best;
+}
+
+bool fos_upload_gram_eligible(const fos_design* h) {
+    if (h->dtype != FOS_F64 || h->d % GT != 0 || h->d > 4096 || h->lda != h->d) return false;
+    const char* e = getenv("FOS_UPLOAD_GRAM");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return h->n >= 16LL * GKB;
+    // automatic: tall designs whose upload is long enough to hide the contraction
+    const double bytes = static_cast<double>(h->n) * h->d * 8.0;
+    return h->n >= 16LL * h->d && bytes >= 1.0e9;
+}
+
+long long fos_upload_gram_chunk_rows(const fos_design* h) {
+    long long rows = (512LL << 20) / (static_cast<long long>(h->d) * 8);
+    rows = std::max<long long>(rows, 64LL * GKB);
+    if (const char* e = getenv("FOS_UPLOAD_GRAM_CHUNK_ROWS")) {  // tests: several chunks on a small design
+        const long long v = atoll(e);
+        if (v >= 1) rows = v;
+    }
+    return std::min<long long>(rows, h->n);
+}
+
+// allocate the split workspace and the result; a failed allocation only disables the feature
+int fos_upload_gram_begin(fos_design* h, cudaStream_t s) {
+    const long long d = h->d;
+    const int nb = h->d / GT, ntiles = nb * (nb + 1) / 2;
+    h->up_nsplit = syrk_pick_split(h, ntiles, fos_upload_gram_chunk_rows(h), d);
+    const size_t wbytes = static_cast<size_t>(h->up_nsplit) * d * d * sizeof(double);
+    if (cudaMalloc(&h->up_W, wbytes) != cudaSuccess || cudaMalloc(&h->G_up, d * d * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        fos_upload_gram_drop(h);
+        return FOS_OK;
+    }
+    FOS_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(syrk_smem_bytes())));
+    FOS_CUDA(cudaMemsetAsync(h->up_W, 0, wbytes, s));
+    return FOS_OK;
+}
+
+int fos_upload_gram_chunk(fos_design* h, long long row0, long long rows, cudaStream_t s) {
+    if (!h->up_W || rows <= 0) return FOS_OK;
+    SyrkArgs a{};
+    a.A = static_cast<const double*>(h->A) + static_cast<size_t>(row0) * h->lda;
+    a.n = rows;
+    a.lda = h->lda;
+    a.nb = h->d / GT;
+    a.ntiles = a.nb * (a.nb + 1) / 2;
+    a.dpad = h->d;
+    a.W = h->up_W;
+    a.accumulate = 1;
+    long long rps = (rows + h->up_nsplit - 1) / h->up_nsplit;
+    a.rows_per_split = (rps + GKB - 1) / GKB * GKB;
+    gram_syrk_kernel<<<dim3(a.ntiles * h->up_nsplit), dim3(256), syrk_smem_bytes(), s>>>(a);
+    FOS_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FOS_OK;
+}
+
+int fos_upload_gram_finish(fos_design* h, cudaStream_t s) {
+    if (!h->up_W) return FOS_OK;
+    const long long d = h->d;
+    gram_reduce_kernel<<<dim3(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d)), dim3(256), 0, s>>>(
+        h->up_W, h->G_up, d, h->up_nsplit);
+    FOS_CUDA(cudaGetLastError());
+    FOS_CUDA(cudaStreamSynchronize(s));
+    cudaFree(h->up_W);
+    h->up_W = nullptr;
+    h->G_state = 1;
+    h->launches += 1;
+    return FOS_OK;
+}
+
+void fos_upload_gram_drop(fos_design* h) {
+    if (h->up_W) cudaFree(h->up_W);
+    if (h->G_up) cudaFree(h->G_up);
+    h->up_W = nullptr;
+    h->G_up = nullptr;
+    h->G_state = 0;
+}
+
+int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out, int* iters_out,
+                        float* gpu_ms_out) {
+    const int d = h->d;
+    GramPowerState* st = nullptr;
+    double* w = nullptr;
+    FOS_CUDA(cudaMalloc(&st, sizeof(GramPowerState)));
+    cudaError_t e = cudaMalloc(&w, static_cast<size_t>(d) * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaFree(st);
+        fos_set_error("cannot allocate the power-iteration workspace");
+        return FOS_ERR_NOMEM;
+    }
+    GramPowerState init{};
+    init.tol = tol;
+    init.pit_max = n_iter;
+    int status = FOS_OK;
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+        // y <- v0 through the pinned staging buffer (the padding of y beyond d stays zero)
+        memcpy(h->vec_host, v0, static_cast<size_t>(d) * sizeof(double));
+        FOS_CUDA(cudaMemcpyAsync(h->y, h->vec_host, static_cast<size_t>(d) * sizeof(double), cudaMemcpyHostToDevice,
+                                 h->stream));
+        FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+        for (int k = 0; k < n_iter; ++k) {
+            gram_matvec_kernel<<<dim3((d + 7) / 8), dim3(256), 0, h->stream>>>(h->G_up, h->y, w, d, st);
+            gram_power_finish_kernel<<<dim3(1), dim3(1024), 0, h->stream>>>(w, h->y, d, st);
+        }
+        FOS_CUDA(cudaGetLastError());
+        h->launches += 2LL * n_iter;
+        FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+        FOS_CUDA(cudaMemcpyAsync(&init, st, sizeof(init), cudaMemcpyDeviceToHost, h->stream));
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        *L_out = init.L;
+        if (iters_out) *iters_out = init.pit;
+        if (gpu_ms_out) FOS_CUDA(cudaEventElapsedTime(gpu_ms_out, h->ev0, h->ev1));
+        return FOS_OK;
+    };
+    status = body();
+    cudaFree(st);
+    cudaFree(w);
+    return status;
+}
+
 extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
     FOS_REQUIRE(h && out, "null pointer argument");
     FOS_REQUIRE(h->dtype == FOS_F64, "Gram mode needs float64 storage");
@@ -387,6 +604,17 @@ extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
         g->bb = 2.0 * half_bb;
         FOS_CUDA(cudaMemcpy(g->c, gneg.data(), static_cast<size_t>(d) * sizeof(double), cudaMemcpyHostToDevice));
 
+        if (h->G_up && h->G_state == 1) {
+            // already accumulated under the upload of this design: copy instead of rebuilding
+            cudaEventRecord(g->ev0, g->stream);
+            FOS_CUDA(cudaMemcpyAsync(g->G, h->G_up, static_cast<size_t>(d) * d * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     g->stream));
+            cudaEventRecord(g->ev1, g->stream);
+            FOS_CUDA(cudaStreamSynchronize(g->stream));
+            FOS_CUDA(cudaEventElapsedTime(&g->build_ms, g->ev0, g->ev1));
+            g->nsplit = h->up_nsplit;
+            return FOS_OK;
+        }
         SyrkArgs a{};
         a.A = static_cast<const double*>(h->A);
         a.n = h->n;

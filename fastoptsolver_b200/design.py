@@ -145,6 +145,23 @@ class DeviceDesign:
                                                  _ptr(np.ascontiguousarray(sd)), float(mean[-1])))
         return mean[:-1], sd, float(mean[-1])
 
+    def upload_gram(self):
+        """Gram matrix accumulated under the host->device upload, if any (include/fos.h,
+        fos_design_upload_gram): dict(ptr, state, copy_ms, tail_ms); state 0 none, 1 local rows,
+        2 summed over all ranks."""
+        g, st, cm, tm = C.c_void_p(), C.c_int(), C.c_float(), C.c_float()
+        _lib.check(_lib.load().fos_design_upload_gram(self.handle, C.byref(g), C.byref(st), C.byref(cm), C.byref(tm)))
+        return {"ptr": g.value, "state": st.value, "copy_ms": cm.value, "tail_ms": tm.value}
+
+    def comm_info(self):
+        """(rank, world) of a row-sharded design; (0, 1) otherwise."""
+        r, w = C.c_int(), C.c_int()
+        _lib.check(_lib.load().fos_comm_info(self.handle, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def set_upload_gram(self, state):
+        _lib.check(_lib.load().fos_design_upload_gram_set(self.handle, int(state)))
+
     def lambda_max(self):
         out = C.c_double()
         _lib.check(_lib.load().fos_design_lambda_max(self.handle, C.byref(out)))
@@ -192,17 +209,25 @@ _CACHE = {}          # key -> (DeviceDesign, fingerprint)
 _CACHE_MAX = 4
 
 
-def _fingerprint(A, b):
-    """Content check for cache reuse: CRC of ~64k strided samples of A, of its first and last
-    rows, and of ALL of b.  (A full CRC of a 32 GB matrix would cost more than re-uploading it.)"""
+def _fingerprint_matrix(A):
+    """Content check of A for cache reuse: CRC of ~64k strided samples and of its first and last
+    rows.  (A full CRC of a 32 GB matrix would cost more than re-uploading it.)"""
     flat_n = A.shape[0] * A.shape[1]
     step = max(1, flat_n // 65536)
     idx = np.arange(0, flat_n, step)
     crc = zlib.crc32(np.ascontiguousarray(A[idx // A.shape[1], idx % A.shape[1]]).tobytes())
     crc = zlib.crc32(np.ascontiguousarray(A[0]).tobytes(), crc)
     crc = zlib.crc32(np.ascontiguousarray(A[-1]).tobytes(), crc)
-    crc = zlib.crc32(np.ascontiguousarray(b).tobytes(), crc)
     return crc
+
+
+def _fingerprint(A, b):
+    """(matrix fingerprint, CRC of ALL of b)."""
+    return _fingerprint_matrix(A), zlib.crc32(np.ascontiguousarray(b).tobytes())
+
+
+def _matrix_key(A):
+    return (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str)
 
 
 def as_design(A, b=None, device=0):
@@ -220,39 +245,44 @@ def as_design(A, b=None, device=0):
     b = np.asarray(b)
     if os.environ.get("FOS_NO_CACHE") == "1":
         return DeviceDesign.from_host(A, b, device=device)
-    key = (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str,
-           b.__array_interface__["data"][0], b.shape, device)
+    key = _matrix_key(A) + (b.__array_interface__["data"][0], b.shape, device)
     fp = _fingerprint(A, b.reshape(-1))
     hit = _CACHE.get(key)
-    if hit is not None and hit[1] == fp and hit[0]._h is not None and hit[2]() is _base_of(A):
+    if hit is not None and hit[1] == fp and hit[0]._h is not None and hit[2]() is A:
         return hit[0]
     des = DeviceDesign.from_host(A, b, device=device)
     if len(_CACHE) >= _CACHE_MAX:
         old_key = next(iter(_CACHE))
         _CACHE.pop(old_key)      # freed by its finalizer once nobody else holds it
     try:
-        ref = weakref.ref(_base_of(A))
+        ref = weakref.ref(A, lambda _r, k=key: _evict(k))   # host array gone: free the HBM copy too
     except TypeError:            # not weak-referenceable: never reuse
         ref = lambda: None       # noqa: E731
     _CACHE[key] = (des, fp, ref)
     return des
 
 
-def _base_of(A):
-    """The object that owns A's memory (np.asarray of an ndarray returns the array itself)."""
-    return A
+def _evict(key):
+    # dropping the entry drops the cache's reference: the device copy is freed by the
+    # DeviceDesign finalizer unless the caller still holds the handle
+    _CACHE.pop(key, None)
 
 
 def find_by_matrix(A, device=0):
-    """A cached design whose matrix is this host array (whatever its b), or None.  Lets
-    ``estimate_lipschitz(A)``, which never reads b, reuse the copy a solver uploaded."""
+    """A cached design whose matrix is this very host array (same object, still alive, same
+    content fingerprint; whatever its b), or None.  Lets ``estimate_lipschitz(A)``, which never
+    reads b, reuse the copy a solver uploaded."""
     if isinstance(A, DeviceDesign):
         return A
     A = np.asarray(A)
-    akey = (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str)
-    for key, (des, _, _r) in _CACHE.items():
-        if key[:4] == akey and key[6] == device and des._h is not None:
-            return des
+    akey = _matrix_key(A)
+    fp_a = None
+    for key, (des, fp, ref) in _CACHE.items():
+        if key[:4] == akey and key[6] == device and des._h is not None and ref() is A:
+            if fp_a is None:
+                fp_a = _fingerprint_matrix(A)
+            if fp[0] == fp_a:
+                return des
     return None
 
 

@@ -8,6 +8,7 @@ Armijo decisions, restarts and stop rules all run on the device.
 from __future__ import annotations
 
 import ctypes as C_
+import time
 from typing import Callable
 
 import numpy as np
@@ -59,7 +60,11 @@ def estimate_lipschitz(A, n_iter: int = 100, tol: float = 1e-6) -> float:
     v = np.random.randn(des.shape[1])
     v /= np.linalg.norm(v)
     L, iters, ms = des.power_iter(v, n_iter, tol)
-    last_run["lipschitz"] = {"iters": iters, "gpu_ms": ms}
+    # "gram": the products ran on G = A^T A accumulated under the upload (include/fos.h,
+    # fos_design_upload_gram); "stream": two fused passes over A per step
+    st, world = des.upload_gram()["state"], des.comm_info()[1]
+    on_gram = (st == 2) if world > 1 else (st == 1)
+    last_run["lipschitz"] = {"iters": iters, "gpu_ms": ms, "via": "gram" if on_gram else "stream"}
     return np.float64(L)
 
 
@@ -241,8 +246,11 @@ def fista(
     """Accelerated proximal gradient (iterative_solvers.py:132-245).  ``reg_type`` is
     accepted and ignored exactly as in the reference; alpha1 > 0 / alpha2 > 0 decide."""
     reset_metrics()
+    t0 = time.perf_counter()
     des = as_design(A, b)
+    t1 = time.perf_counter()
     L_val = estimate_lipschitz(des)
+    t2 = time.perf_counter()
     if alpha2 > 0:
         L_val += alpha2
     last_run["L"] = float(L_val)
@@ -252,6 +260,10 @@ def fista(
         backtracking=backtracking, eta=eta, step0=t_init_factor / L_val, max_iter=max_iter, tol=tol,
         tol_ratio=tol_ratio, adaptive_restart=adaptive_restart, restart_threshold=restart_threshold,
         want_history=return_history)
+    t3 = time.perf_counter()
+    # host wall clock of the stages of this call (seconds): design lookup / upload, Lipschitz
+    # estimate, solver loop incl. result download
+    last_run["host_s"] = {"design": t1 - t0, "lipschitz": t2 - t1, "solve": t3 - t2}
     if not return_history:
         return x
     history = {"x": [xh[i].copy() for i in range(it + 1)], "obj": [np.float64(v) for v in oh[:it]]}

@@ -60,7 +60,37 @@ def sharded_from_host(A_local, b_local, dist, group=None, device=None):
         device = torch.cuda.current_device()
     des = DeviceDesign.from_host(A_local, b_local, device=device)
     attach(des, dist, group)
+    allreduce_upload_gram(des, dist, group)
     return des
+
+
+def allreduce_upload_gram(des: DeviceDesign, dist, group=None):
+    """If every rank accumulated the Gram matrix of its rows under the upload (include/fos.h,
+    fos_design_upload_gram), sum them over the ranks in place -- d^2 doubles, once, a plain library
+    all-reduce -- so that ``estimate_lipschitz`` iterates on G instead of streaming A; if any
+    rank has none, all ranks discard theirs and keep the streaming power iteration."""
+    import torch
+    info = des.upload_gram()
+    if "nccl" not in str(dist.get_backend(group)):
+        # no device collective on this group (same answer on every rank): keep streaming
+        if info["state"] != 0:
+            des.set_upload_gram(0)
+        return False
+    dev = f"cuda:{des.device}"
+    flag = torch.tensor([1 if info["state"] == 1 else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        if info["state"] != 0:
+            des.set_upload_gram(0)
+        return False
+    d = des.shape[1]
+    arr = type("_G", (), {"__cuda_array_interface__": {"shape": (d, d), "typestr": "<f8", "data": (int(info["ptr"]), False),
+                                                       "version": 3, "strides": None}})()
+    G = torch.as_tensor(arr, device=dev)
+    dist.all_reduce(G, group=group)
+    torch.cuda.synchronize(G.device)
+    des.set_upload_gram(2)
+    return True
 
 
 def sharded_synthetic(n_total, d, dist, group=None, device=None, dtype=np.float64, **scenario):

@@ -94,6 +94,18 @@ int fos_design_shape(const fos_design* h, int64_t* n, int64_t* d, int* dtype, in
 int fos_design_download(fos_design* h, int64_t row0, int64_t rows, void* A_out, double* b_out);
 /* device pointers of the resident arrays (for zero-copy wrappers) */
 int fos_design_pointers(fos_design* h, void** A_dev, double** b_dev);
+/* Gram matrix accumulated under the upload.  fos_design_create copies a dense float64 C-order
+ * design with n >= 16 d, d a multiple of 128 and <= 4096, >= 1 GB (FOS_UPLOAD_GRAM=1/0 forces it
+ * on/off) in 512 MB row chunks and runs the tensor-core SYRK of fos_gram_create on every chunk
+ * that has arrived, on a second stream: G = A^T A of the local rows is complete a few ms after
+ * the last byte.  fos_power_iter (estimate_lipschitz, iterative_solvers.py:45-60) then iterates
+ * w = G v instead of w = A^T(A v): the same numbers up to rounding (relative 1e-15 on L), 100 x
+ * d^2 instead of 100 x n d doubles of traffic.  fos_gram_create reuses the matrix as well.
+ * state: 0 none, 1 local rows, 2 summed over all ranks.  Row-sharded callers all-reduce *G_dev
+ * in place and then call fos_design_upload_gram_set(h, 2); until then sharded designs keep the
+ * streaming power iteration.  fos_design_upload_gram_set(h, 0) discards the matrix. */
+int fos_design_upload_gram(fos_design* h, double** G_dev, int* state, float* copy_ms, float* tail_ms);
+int fos_design_upload_gram_set(fos_design* h, int state);
 /* Column statistics of the resident design (one pass over A): out[c] = sum_i (A[i][c] - center[c])^p
  * with p = 2 if `squared` else 1 (center may be NULL = 0; it has d+1 entries, the last for b);
  * *b_out gets the same statistic of b.  Local rows only: sharded callers add the ranks' results. */
