@@ -136,8 +136,30 @@ def pick_sample_rows(n, d, requested):
 
 
 # ------------------------------------------------------------------------------- main
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that write to file descriptor 1 themselves
+    (NCCL prints its version banner there) are sent to stderr for the rest of the run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -294,7 +316,7 @@ def main():
             "gradient_only_it_s": res["grad_it_s"],
         }
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
     des.close()
@@ -352,7 +374,8 @@ def e2e_run(des, alpha1, K, n, d, dist, local_rank):
             "wall_s": wall, "upload_s": upload_s, "h2d_GBps": (h2d / upload_s / 1e9) if upload_s else None,
             "loop_ms": info["loop_ms"], "lipschitz_ms": lip["gpu_ms"],
             "lipschitz_iters": lip["iters"], "lipschitz_via": lip.get("via"),
-            "upload_gram": gram_info, "host_s": dict(S.last_run.get("host_s", {})), "bytes_are": "per rank",
+            "upload_gram": gram_info, "host_s": dict(S.last_run.get("host_s", {})),
+            "solve_host_ms": info.get("host_ms"), "bytes_are": "per rank",
             "what": "fista(A, b, 'lasso', a1, 0, max_iter=K, return_history=True) on pinned host numpy "
                     "arrays (each rank its row block): upload of A+b (with G = A^T A accumulated under the "
                     "copy on the tensor cores when lipschitz_via == 'gram'), <=100-step Lipschitz estimate, K "
@@ -387,7 +410,7 @@ def reference_arm(args, world, rank, local_rank, config, K, W):
                             "gradient_only_it_s": res["grad_it_s"]},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

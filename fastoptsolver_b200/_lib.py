@@ -54,6 +54,7 @@ class PGResult(C.Structure):
         ("stop_reason", C.c_int), ("loop_ms", C.c_float), ("kernel_launches", C.c_int64),
         ("grad_kernel_ms", C.c_float), ("grad_kernel_launches", C.c_int),
         ("epilogue_ms", C.c_float), ("exchange_ms", C.c_float),
+        ("host_setup_ms", C.c_float), ("host_loop_ms", C.c_float), ("host_finish_ms", C.c_float),
     ]
 
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "fos_common.cuh"
@@ -139,6 +140,7 @@ static int design_alloc_work(fos_design* h) {
     FOS_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(FosCtrl), h->stream));
     FOS_CUDA(cudaMallocHost(&h->ctrl_host, 4 * sizeof(FosCtrl)));
     FOS_CUDA(cudaMallocHost(&h->vec_host, (2 * static_cast<size_t>(h->ldv) + 16) * sizeof(double)));
+    FOS_CUDA(cudaMallocHost(&h->pin_scratch, FOS_PIN_SCRATCH));
     memset(h->ctrl_host, 0, 4 * sizeof(FosCtrl));
     FOS_CUDA(cudaStreamSynchronize(h->stream));
     {
@@ -270,11 +272,12 @@ static void design_free(fos_design* h) {
     if (h->owns_A && h->A) cudaFree(h->A);
     if (h->owns_b && h->b) cudaFree(h->b);
     fos_upload_gram_drop(h);
-    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl, h->row_lo, h->sm_slot};
+    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl, h->row_lo, h->sm_slot, h->arena};
     for (void* p : bufs)
         if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->vec_host) cudaFreeHost(h->vec_host);
+    if (h->pin_scratch) cudaFreeHost(h->pin_scratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -792,26 +795,26 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     return FOS_OK;
 }
 
+int fos_arena_reserve(fos_design* h, size_t bytes, void** base) {
+    if (bytes > h->arena_bytes) {
+        if (h->arena) cudaFree(h->arena);
+        h->arena = nullptr;
+        h->arena_bytes = 0;
+        const size_t want = (bytes + (1u << 20) - 1) & ~static_cast<size_t>((1u << 20) - 1);
+        if (cudaMalloc(&h->arena, want) != cudaSuccess) {
+            cudaGetLastError();
+            fos_set_error("cannot allocate %zu bytes of solver workspace on the device", want);
+            return FOS_ERR_NOMEM;
+        }
+        h->arena_bytes = want;
+    }
+    *base = h->arena;
+    return FOS_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // proximal-gradient engine
 // ------------------------------------------------------------------------------------------
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    int alloc(size_t count) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            fos_set_error("cannot allocate %zu bytes of history on the device", count * sizeof(T));
-            return FOS_ERR_NOMEM;
-        }
-        return FOS_OK;
-    }
-};
-
 extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r) {
     FOS_REQUIRE(h && p && r, "null pointer argument");
     FOS_REQUIRE(p->scheme >= 0 && p->scheme <= 2, "unknown scheme %d", p->scheme);
@@ -827,22 +830,34 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     const bool want_obj = want_hist;
     const long long launches0 = h->launches;
 
-    // ---- per-solve device arrays
-    DevBuf<double> xh, oh, th, sh;
-    DevBuf<int> li;
-    DevBuf<float> gm, lm;
-    if (want_hist) FOS_TRY(xh.alloc(static_cast<size_t>(K + 1) * d));
-    FOS_TRY(oh.alloc(K));
-    FOS_TRY(th.alloc(K + 1));
-    FOS_TRY(sh.alloc(K));
-    FOS_TRY(li.alloc(K));
-    FOS_TRY(gm.alloc(K + 1));
-    FOS_TRY(lm.alloc(K));
-    FOS_CUDA(cudaMemsetAsync(li.p, 0, std::max(K, 1) * sizeof(int), h->stream));
-    FOS_CUDA(cudaMemsetAsync(gm.p, 0, (K + 1) * sizeof(float), h->stream));
-    FOS_CUDA(cudaMemsetAsync(lm.p, 0, std::max(K, 1) * sizeof(float), h->stream));
-    FOS_CUDA(cudaMemsetAsync(oh.p, 0, std::max(K, 1) * sizeof(double), h->stream));
-    FOS_CUDA(cudaMemsetAsync(sh.p, 0, std::max(K, 1) * sizeof(double), h->stream));
+    // ---- per-solve device arrays: carved out of one grow-only arena owned by the design
+    // (cudaMalloc / cudaFree per solve cost milliseconds each once peer mappings exist)
+    const auto t_host0 = std::chrono::steady_clock::now();
+    struct Carve {
+        size_t off = 0;
+        size_t take(size_t bytes) {
+            const size_t o = off;
+            off += (bytes + 255) & ~static_cast<size_t>(255);
+            return o;
+        }
+    } cv;
+    const size_t K1 = static_cast<size_t>(std::max(K, 1));
+    const size_t o_xh = cv.take(want_hist ? static_cast<size_t>(K + 1) * d * sizeof(double) : 0);
+    const size_t o_oh = cv.take(K1 * sizeof(double));
+    const size_t o_th = cv.take((K1 + 1) * sizeof(double));
+    const size_t o_sh = cv.take(K1 * sizeof(double));
+    const size_t o_li = cv.take(K1 * sizeof(int));
+    const size_t o_gm = cv.take((K1 + 1) * sizeof(float));
+    const size_t o_lm = cv.take(K1 * sizeof(float));
+    void* arena_base = nullptr;
+    FOS_TRY(fos_arena_reserve(h, cv.off, &arena_base));
+    char* base = static_cast<char*>(arena_base);
+    struct { double* p; } xh{reinterpret_cast<double*>(base + o_xh)}, oh{reinterpret_cast<double*>(base + o_oh)},
+        th{reinterpret_cast<double*>(base + o_th)}, sh{reinterpret_cast<double*>(base + o_sh)};
+    struct { int* p; } li{reinterpret_cast<int*>(base + o_li)};
+    struct { float* p; } gm{reinterpret_cast<float*>(base + o_gm)}, lm{reinterpret_cast<float*>(base + o_lm)};
+    // everything after the iterate history is zeroed in one go (objectives, steps, counts, timings)
+    FOS_CUDA(cudaMemsetAsync(base + o_oh, 0, cv.off - o_oh, h->stream));
     FosHist hist{};
     hist.x_hist = want_hist ? xh.p : nullptr;
     hist.obj_hist = oh.p;
@@ -903,11 +918,13 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
         }
     }
     FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    const auto t_host1 = std::chrono::steady_clock::now();
     long long pairs = 0;
     if (K > 0)
         FOS_TRY(drive_passes(h, EOP_PG, hist, max_pairs, [](const FosCtrl& s) { return s.phase == PH_DONE; }, &pairs,
                              exact));
     FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    const auto t_host2 = std::chrono::steady_clock::now();
 
     // ---- results
     FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
@@ -950,6 +967,10 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
         r->grad_kernel_ms += ms;
         r->grad_kernel_launches += 1;
     }
+    const auto t_host3 = std::chrono::steady_clock::now();
+    r->host_setup_ms = std::chrono::duration<float, std::milli>(t_host1 - t_host0).count();
+    r->host_loop_ms = std::chrono::duration<float, std::milli>(t_host2 - t_host1).count();
+    r->host_finish_ms = std::chrono::duration<float, std::milli>(t_host3 - t_host2).count();
     return FOS_OK;
 }
 

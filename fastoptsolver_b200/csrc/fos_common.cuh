@@ -190,6 +190,9 @@ struct fos_design {
     int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed
     bool balanced = false;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
+    void* arena = nullptr;         // grow-only device workspace of the per-solve arrays (fos_arena_reserve)
+    size_t arena_bytes = 0;
+    void* pin_scratch = nullptr;   // FOS_PIN_SCRATCH bytes of pinned host memory for control-block snapshots
     // Gram matrix of the local rows accumulated under the host->device upload (gram_kernels.cu)
     double* G_up = nullptr;   // [d][d], owned
     int G_state = 0;          // 0 none, 1 local rows, 2 summed over all ranks by the caller
@@ -201,6 +204,12 @@ struct fos_design {
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
     size_t prof_used = 0;
 };
+
+constexpr size_t FOS_PIN_SCRATCH = 16384;
+// Grow-only per-design device workspace: solver calls carve their per-call arrays out of it
+// instead of cudaMalloc/cudaFree pairs (milliseconds each once peer mappings exist).  The
+// previous contents are lost when it grows; one solver call at a time per design.
+int fos_arena_reserve(fos_design* h, size_t bytes, void** base);
 
 // launchers implemented in the .cu files
 cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args,

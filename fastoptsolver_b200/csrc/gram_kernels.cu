@@ -541,15 +541,10 @@ void fos_upload_gram_drop(fos_design* h) {
 int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out, int* iters_out,
                         float* gpu_ms_out) {
     const int d = h->d;
-    GramPowerState* st = nullptr;
-    double* w = nullptr;
-    FOS_CUDA(cudaMalloc(&st, sizeof(GramPowerState)));
-    cudaError_t e = cudaMalloc(&w, static_cast<size_t>(d) * sizeof(double));
-    if (e != cudaSuccess) {
-        cudaFree(st);
-        fos_set_error("cannot allocate the power-iteration workspace");
-        return FOS_ERR_NOMEM;
-    }
+    void* base = nullptr;
+    FOS_TRY(fos_arena_reserve(h, 256 + static_cast<size_t>(d) * sizeof(double), &base));
+    GramPowerState* st = static_cast<GramPowerState*>(base);
+    double* w = reinterpret_cast<double*>(static_cast<char*>(base) + 256);
     GramPowerState init{};
     init.tol = tol;
     init.pit_max = n_iter;
@@ -576,8 +571,6 @@ int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol,
         return FOS_OK;
     };
     status = body();
-    cudaFree(st);
-    cudaFree(w);
     return status;
 }
 

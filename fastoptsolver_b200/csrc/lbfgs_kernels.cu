@@ -552,19 +552,21 @@ extern "C" int fos_lbfgs(fos_design* h, const fos_lbfgs_params* p, fos_lbfgs_res
     double *S = nullptr, *Y = nullptr, *x = nullptr, *gacc = nullptr, *dvec = nullptr, *oh = nullptr;
     LbfgsCtrl* L = nullptr;
     const long long launches0 = h->launches;
-    auto cleanup = [&]() {
-        for (void* q : {static_cast<void*>(S), static_cast<void*>(Y), static_cast<void*>(x), static_cast<void*>(gacc),
-                        static_cast<void*>(dvec), static_cast<void*>(oh), static_cast<void*>(L)})
-            if (q) cudaFree(q);
-    };
+    static_assert(2 * sizeof(LbfgsCtrl) <= FOS_PIN_SCRATCH, "pinned scratch too small for the L-BFGS snapshots");
+    auto cleanup = [&]() {};
     auto body = [&]() -> int {
-        FOS_CUDA(cudaMalloc(&S, vb * p->m));
-        FOS_CUDA(cudaMalloc(&Y, vb * p->m));
-        FOS_CUDA(cudaMalloc(&x, vb));
-        FOS_CUDA(cudaMalloc(&gacc, vb));
-        FOS_CUDA(cudaMalloc(&dvec, vb));
-        FOS_CUDA(cudaMalloc(&oh, static_cast<size_t>(std::max(p->max_iter, 1)) * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&L, sizeof(LbfgsCtrl)));
+        // per-call arrays from the design's grow-only workspace (no cudaMalloc / cudaFree per fit)
+        const size_t ohb = (static_cast<size_t>(std::max(p->max_iter, 1)) * sizeof(double) + 255) & ~static_cast<size_t>(255);
+        const size_t lcb = (sizeof(LbfgsCtrl) + 255) & ~static_cast<size_t>(255);
+        void* base = nullptr;
+        FOS_TRY(fos_arena_reserve(h, vb * (2 * static_cast<size_t>(p->m) + 3) + ohb + lcb, &base));
+        S = static_cast<double*>(base);
+        Y = S + static_cast<size_t>(p->m) * h->ldv;
+        x = Y + static_cast<size_t>(p->m) * h->ldv;
+        gacc = x + h->ldv;
+        dvec = gacc + h->ldv;
+        oh = dvec + h->ldv;
+        L = reinterpret_cast<LbfgsCtrl*>(reinterpret_cast<char*>(oh) + ohb);
         for (double* q : {S, Y}) FOS_CUDA(cudaMemsetAsync(q, 0, vb * p->m, h->stream));
         for (double* q : {x, gacc, dvec}) FOS_CUDA(cudaMemsetAsync(q, 0, vb, h->stream));
         LbfgsCtrl lc{};
@@ -616,8 +618,8 @@ extern "C" int fos_lbfgs(fos_design* h, const fos_lbfgs_params* p, fos_lbfgs_res
 
         FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
         // launch passes in batches; poll the (small) L-BFGS control block between batches
-        LbfgsCtrl* snap = nullptr;
-        FOS_CUDA(cudaMallocHost(&snap, 2 * sizeof(LbfgsCtrl)));
+        LbfgsCtrl* snap = static_cast<LbfgsCtrl*>(h->pin_scratch);
+        memset(snap, 0, 2 * sizeof(LbfgsCtrl));
         cudaEvent_t ev[2];
         cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
@@ -655,7 +657,6 @@ extern "C" int fos_lbfgs(fos_design* h, const fos_lbfgs_params* p, fos_lbfgs_res
         cudaError_t se = cudaStreamSynchronize(h->stream);
         cudaEventDestroy(ev[0]);
         cudaEventDestroy(ev[1]);
-        cudaFreeHost(snap);
         if (status != FOS_OK) return status;
         if (se != cudaSuccess) {
             fos_set_error("L-BFGS loop failed: %s", cudaGetErrorString(se));

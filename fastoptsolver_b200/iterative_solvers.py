@@ -141,6 +141,7 @@ def _run(des, *, scheme, alpha1, alpha2, obj_terms, delta, backtracking, eta, st
         "loop_ms": r.loop_ms, "kernel_launches": r.kernel_launches,
         "grad_kernel_ms": r.grad_kernel_ms, "grad_kernel_launches": r.grad_kernel_launches,
         "epilogue_ms": r.epilogue_ms, "exchange_ms": r.exchange_ms,
+        "host_ms": {"setup": r.host_setup_ms, "loop": r.host_loop_ms, "finish": r.host_finish_ms},
     }
     return x, it, xh, oh, th, sh
 

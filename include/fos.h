@@ -199,6 +199,9 @@ typedef struct fos_pg_result {
      * part of it spent publishing to / waiting for the peer ranks (0 on one GPU) */
     float epilogue_ms;
     float exchange_ms;
+    /* host wall clock of the call: workspace + state upload, launching and waiting for the loop,
+     * downloading the results */
+    float host_setup_ms, host_loop_ms, host_finish_ms;
 } fos_pg_result;
 
 int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_result* r);

@@ -114,6 +114,41 @@ def _worker(rank, world, port, q):
         assert abs(gram.btb - b @ b) <= 1e-12 * (b @ b)
         gram.close()
         shard.close()
+        # Gram accumulated under each rank's upload, summed over the ranks (forced on for this
+        # small shape): estimate_lipschitz on it == the streaming estimate == numpy, all ranks equal
+        rng = np.random.default_rng(2)
+        A = rng.standard_normal((world * 6000 + 13, 256))
+        A[:, ::4] *= 2.0
+        b = rng.standard_normal(A.shape[0])
+        lo, hi = multigpu.shard_bounds(A.shape[0], rank, world)
+        os.environ["FOS_UPLOAD_GRAM"] = "1"
+        shard = multigpu.sharded_from_host(np.ascontiguousarray(A[lo:hi]), b[lo:hi], dist, device=rank)
+        os.environ["FOS_UPLOAD_GRAM"] = "0"
+        plain = multigpu.sharded_from_host(np.ascontiguousarray(A[lo:hi]), b[lo:hi], dist, device=rank)
+        os.environ.pop("FOS_UPLOAD_GRAM")
+        assert shard.upload_gram()["state"] == 2 and plain.upload_gram()["state"] == 0
+        import oracle
+        np.random.seed(3)
+        L_ref = oracle.estimate_lipschitz(A)
+        np.random.seed(3)
+        L_g = S.estimate_lipschitz(shard)
+        assert S.last_run["lipschitz"]["via"] == "gram"
+        np.random.seed(3)
+        L_s = S.estimate_lipschitz(plain)
+        assert S.last_run["lipschitz"]["via"] == "stream"
+        assert abs(L_g - L_ref) <= 1e-12 * L_ref and abs(L_s - L_ref) <= 1e-12 * L_ref
+        t = torch.tensor([L_g], dtype=torch.float64).cuda()
+        lst = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(lst, t)
+        assert all(torch.equal(lst[0], v) for v in lst), "ranks hold different Lipschitz estimates"
+        np.random.seed(0)
+        xg, hg = S.fista(shard, None, "lasso", 50.0, 0.0, max_iter=25, return_history=True)
+        np.random.seed(0)
+        xr, hr = oracle.fista(A, b, "lasso", 50.0, 0.0, max_iter=25, return_history=True)
+        assert harness.rel_err(xg, xr) <= 1e-10
+        np.testing.assert_allclose(hg["obj"], hr["obj"], rtol=1e-10)
+        multigpu.close(shard, dist)
+        multigpu.close(plain, dist)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
