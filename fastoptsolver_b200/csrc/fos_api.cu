@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "fos_common.cuh"
@@ -312,24 +314,151 @@ static int alloc_matrix(fos_design* h) {
     return FOS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// host -> device copies of the design
+// ------------------------------------------------------------------------------------------
+// The reference's callers hand over plain numpy arrays, i.e. PAGEABLE memory, which
+// cudaMemcpy moves through a single driver-side staging buffer at a fraction of the PCIe
+// rate.  Large pageable sources are therefore copied by HostStager: T threads each memcpy their
+// share of the pieces into their own pair of pinned slots and push them to the device on
+// their own stream, so host memcpy and PCIe transfers of different pieces overlap.  Pinned
+// (cudaHostAlloc / cudaHostRegister) sources go straight through cudaMemcpyAsync.
+namespace {
+
+struct HostStager {
+    static constexpr int T = 16;                // most copy threads (FOS_UPLOAD_THREADS, default 8)
+    static constexpr int NSLOT = 2;             // pinned slots per thread (double buffer)
+    static constexpr size_t SLOT = 8u << 20;    // bytes per slot
+    static constexpr size_t MIN_BYTES = 128u << 20;  // below this a plain cudaMemcpyAsync is used
+
+    // process-wide pinned slots, allocated on first use and kept (pinning 128 MB costs ~50 ms)
+    static void* slots(int t, int s) {
+        static std::mutex mu;
+        static void* base = nullptr;
+        static bool tried = false;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!tried) {
+            tried = true;
+            if (cudaMallocHost(&base, static_cast<size_t>(T) * NSLOT * SLOT) != cudaSuccess) {
+                cudaGetLastError();
+                base = nullptr;
+            }
+        }
+        return base ? static_cast<char*>(base) + (static_cast<size_t>(t) * NSLOT + s) * SLOT : nullptr;
+    }
+
+    int device = 0;
+    int threads = 8;
+    cudaStream_t stream[T] = {};
+    cudaEvent_t slot_ev[T][NSLOT] = {};
+    cudaEvent_t done_ev[T] = {};
+    int next_slot[T] = {};
+    bool ready = false;
+
+    int init(int dev) {
+        device = dev;
+        if (slots(0, 0) == nullptr) return FOS_OK;  // no pinned memory: stay on the plain path
+        if (const char* e = getenv("FOS_UPLOAD_THREADS")) threads = std::max(1, std::min(T, atoi(e)));
+        for (int t = 0; t < threads; ++t) {
+            FOS_CUDA(cudaStreamCreateWithFlags(&stream[t], cudaStreamNonBlocking));
+            FOS_CUDA(cudaEventCreateWithFlags(&done_ev[t], cudaEventDisableTiming));
+            for (int q = 0; q < NSLOT; ++q) FOS_CUDA(cudaEventCreateWithFlags(&slot_ev[t][q], cudaEventDisableTiming));
+        }
+        ready = true;
+        return FOS_OK;
+    }
+    void drain() {
+        for (int t = 0; t < T; ++t)
+            if (stream[t]) cudaStreamSynchronize(stream[t]);
+    }
+    ~HostStager() {
+        drain();
+        for (int t = 0; t < T; ++t) {
+            if (stream[t]) cudaStreamDestroy(stream[t]);
+            if (done_ev[t]) cudaEventDestroy(done_ev[t]);
+            for (int q = 0; q < NSLOT; ++q)
+                if (slot_ev[t][q]) cudaEventDestroy(slot_ev[t][q]);
+        }
+    }
+
+    static bool pageable(const void* p) {
+        const char* e = getenv("FOS_UPLOAD_STAGED");  // "0": never stage, "1": stage even pinned sources (tests)
+        if (e && e[0] == '1') return true;
+        if (e && e[0] == '0') return false;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return true;
+        }
+        return at.type == cudaMemoryTypeUnregistered;
+    }
+
+    // Equivalent of cudaMemcpyAsync(dst, src, bytes, HostToDevice, order_on): when it returns the
+    // source has been read completely and `order_on` is ordered after the last device copy.
+    int copy(void* dst, const void* src, size_t bytes, cudaStream_t order_on) {
+        const char* e = getenv("FOS_UPLOAD_STAGED");
+        const bool force = e && e[0] == '1';
+        if (!ready || (!force && bytes < MIN_BYTES) || !pageable(src)) {
+            FOS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, order_on));
+            return FOS_OK;
+        }
+        const size_t pieces = (bytes + SLOT - 1) / SLOT;
+        std::atomic<int> err{static_cast<int>(cudaSuccess)};
+        auto work = [&](int t) {
+            cudaSetDevice(device);
+            for (size_t p = t; p < pieces && err.load() == cudaSuccess; p += threads) {
+                const int q = next_slot[t];
+                next_slot[t] ^= 1;
+                cudaError_t ce = cudaEventSynchronize(slot_ev[t][q]);  // the slot's previous copy has left
+                const size_t off = p * SLOT, len = std::min(SLOT, bytes - off);
+                void* st = slots(t, q);
+                memcpy(st, static_cast<const char*>(src) + off, len);
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync(static_cast<char*>(dst) + off, st, len, cudaMemcpyHostToDevice, stream[t]);
+                if (ce == cudaSuccess) ce = cudaEventRecord(slot_ev[t][q], stream[t]);
+                if (ce != cudaSuccess) err.store(static_cast<int>(ce));
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        if (err.load() != cudaSuccess) {
+            fos_set_error("staged upload failed: %s", cudaGetErrorString(static_cast<cudaError_t>(err.load())));
+            return FOS_ERR_CUDA;
+        }
+        for (int t = 0; t < threads; ++t) {
+            FOS_CUDA(cudaEventRecord(done_ev[t], stream[t]));
+            FOS_CUDA(cudaStreamWaitEvent(order_on, done_ev[t], 0));
+        }
+        return FOS_OK;
+    }
+};
+
+}  // namespace
+
 // Chunked H2D copy of a dense float64 C-order matrix with the Gram accumulation of the arrived
 // rows running underneath on a second stream.  Copy stream: h->stream.
-static int upload_with_gram(fos_design* h, const void* A) {
+static int upload_dense(fos_design* h, const void* A, HostStager& stager, bool with_gram) {
     cudaStream_t cs = nullptr;
     FOS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     std::vector<cudaEvent_t> evs;
     cudaEvent_t t_done = nullptr;
     auto body = [&]() -> int {
-        FOS_TRY(fos_upload_gram_begin(h, cs));
-        const long long chunk = fos_upload_gram_chunk_rows(h);
-        const size_t row_bytes = static_cast<size_t>(h->d) * sizeof(double);
+        if (with_gram) FOS_TRY(fos_upload_gram_begin(h, cs));
+        const size_t row_bytes = static_cast<size_t>(h->lda) * (h->dtype == FOS_F64 ? 8 : 4);
+        // 512 MB row chunks in every case: one giant cudaMemcpyAsync pays its whole DMA set-up
+        // before the first byte moves (~70 ms for 8 GB), chunks pipeline it
+        const long long chunk = with_gram ? fos_upload_gram_chunk_rows(h)
+                                          : std::max<long long>(1, (512LL << 20) / static_cast<long long>(row_bytes));
         FOS_CUDA(cudaEventCreate(&t_done));
         FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
         for (long long r0 = 0; r0 < h->n; r0 += chunk) {
             const long long rows = std::min<long long>(chunk, h->n - r0);
-            FOS_CUDA(cudaMemcpyAsync(static_cast<char*>(h->A) + static_cast<size_t>(r0) * row_bytes,
-                                     static_cast<const char*>(A) + static_cast<size_t>(r0) * row_bytes,
-                                     static_cast<size_t>(rows) * row_bytes, cudaMemcpyHostToDevice, h->stream));
+            FOS_TRY(stager.copy(static_cast<char*>(h->A) + static_cast<size_t>(r0) * row_bytes,
+                                static_cast<const char*>(A) + static_cast<size_t>(r0) * row_bytes,
+                                static_cast<size_t>(rows) * row_bytes, h->stream));
             if (h->up_W) {
                 cudaEvent_t e;
                 FOS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -365,21 +494,26 @@ extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int6
                                  int64_t row_stride, int64_t col_stride, int device, fos_design** out) {
     FOS_REQUIRE(A && b && out, "null pointer argument");
     fos_design* h = new fos_design();
+    const auto t0 = std::chrono::steady_clock::now();
     FOS_TRY_FREE(h, design_common_init(h, n, d, dtype, device));
+    const auto t1 = std::chrono::steady_clock::now();
     FOS_TRY_FREE(h, alloc_matrix(h));
+    const auto t2 = std::chrono::steady_clock::now();
     const size_t es = elem_size(dtype);
+    HostStager stager;
     auto body = [&]() -> int {
-        FOS_CUDA(cudaMemcpyAsync(h->b, b, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FOS_TRY(stager.init(device));
+        FOS_TRY(stager.copy(h->b, b, static_cast<size_t>(n) * sizeof(double), h->stream));
         if (col_stride == 1 && row_stride >= d) {
             // C order (possibly with a row pitch): strided copy straight into the padded layout
             if (h->lda == d && row_stride == d && fos_upload_gram_eligible(h)) {
                 // dense float64, tall: copy in row chunks and push every chunk that has arrived
                 // through the SYRK kernel on a second stream -- G = A^T A is ready a few ms after
                 // the last byte (gram_kernels.cu), and estimate_lipschitz then iterates on G
-                FOS_TRY(upload_with_gram(h, A));
+                FOS_TRY(upload_dense(h, A, stager, true));
             } else if (h->lda == d && row_stride == d) {
-                // dense on both sides: one linear copy (full PCIe rate from pinned memory)
-                FOS_CUDA(cudaMemcpyAsync(h->A, A, static_cast<size_t>(n) * d * es, cudaMemcpyHostToDevice, h->stream));
+                // dense on both sides: linear copies at the full PCIe rate
+                FOS_TRY(upload_dense(h, A, stager, false));
             } else {
             if (h->lda != d)
                 FOS_CUDA(cudaMemsetAsync(h->A, 0, static_cast<size_t>(n) * h->lda * es, h->stream));
@@ -419,8 +553,18 @@ extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int6
         FOS_CUDA(cudaStreamSynchronize(h->stream));
         return FOS_OK;
     };
-    FOS_TRY_FREE(h, body());
+    const int st_body = body();
+    stager.drain();  // no copy may be in flight when the matrix is freed on the error path
+    FOS_TRY_FREE(h, st_body);
+    const auto t3 = std::chrono::steady_clock::now();
     FOS_TRY_FREE(h, design_alloc_work(h));
+    if (getenv("FOS_UPLOAD_DEBUG")) {
+        const auto t4 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[fos] design_create %lld x %lld: init %.1f ms, cudaMalloc %.1f ms, copy %.1f ms (device %.1f), "
+                        "workspaces %.1f ms\n", static_cast<long long>(n), static_cast<long long>(d), ms(t0, t1), ms(t1, t2),
+                ms(t2, t3), h->up_copy_ms, ms(t3, t4));
+    }
     *out = h;
     return FOS_OK;
 }

@@ -159,3 +159,33 @@ def test_automatic_threshold_and_invalidation():
     des32 = D.DeviceDesign.from_host(A[:70000].astype(np.float32), b[:70000])
     assert des32.upload_gram()["state"] == 0
     des32.close()
+
+
+@pytest.mark.parametrize("n,d,dtype", [(70001, 37, np.float64), (40000, 640, np.float32), (3, 5, np.float64),
+                                       (300000, 128, np.float64)])
+def test_staged_upload_of_pageable_arrays(monkeypatch, n, d, dtype):
+    """The threaded pinned-staging copy used for large pageable (plain numpy) sources delivers the
+    same bytes as the direct copy: forced on for small shapes, ragged last piece, padded leading
+    dimension (odd d goes through the strided path and must be unaffected), with and without the
+    Gram accumulation riding on it."""
+    from fastoptsolver_b200 import design as D
+    D.clear_cache()
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((n, d)).astype(dtype)
+    b = rng.standard_normal(n)
+    monkeypatch.setenv("FOS_UPLOAD_STAGED", "1")
+    for gram in ("0", "1"):
+        monkeypatch.setenv("FOS_UPLOAD_GRAM", gram)
+        des = D.DeviceDesign.from_host(A, b)
+        A2, b2 = des.download()
+        assert A2.tobytes() == A.tobytes() and b2.tobytes() == b.tobytes()
+        if gram == "1" and dtype == np.float64 and d % 128 == 0:
+            assert des.upload_gram()["state"] == 1
+            from fastoptsolver_b200.gram import GramDesign
+            G, _ = GramDesign(des).download()
+            assert harness.rel_err(G, A.T @ A) <= 1e-13
+        x = rng.standard_normal(d)
+        loss, g = des.grad(x)
+        r = A.astype(np.float64) @ x - b
+        assert harness.rel_err(g, A.astype(np.float64).T @ r) <= 1e-12
+        des.close()

@@ -1,13 +1,42 @@
 #!/usr/bin/env python
-"""Host->device bandwidth from pinned memory (what bounds the e2e upload)."""
+"""Host->device bandwidth of the design upload: pinned source, pageable source through the
+driver's own staging (FOS_UPLOAD_STAGED=0) and through the threaded pinned-staging copy."""
+import os
+import sys
 import time
+
+import numpy as np
 import torch
-n = 4 << 30
-h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-d = torch.empty(n, dtype=torch.uint8, device="cuda")
-for _ in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(h, non_blocking=True); torch.cuda.synchronize()
-    print(f"H2D pinned 4 GiB: {n / (time.perf_counter() - t0) / 1e9:.1f} GB/s")
-import subprocess
-print(subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True).stdout[:600])
-print(subprocess.run(["bash", "-c", "nproc; numactl -H 2>/dev/null | head -5; cat /sys/devices/system/node/online"], capture_output=True, text=True).stdout)
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fastoptsolver_b200.design import DeviceDesign  # noqa: E402
+
+os.environ["FOS_UPLOAD_GRAM"] = os.environ.get("FOS_UPLOAD_GRAM", "0")
+n, d = 250000, 4096          # 8.2 GB
+gb = n * d * 8 / 1e9
+b = np.zeros(n)
+A_pin = torch.empty((n, d), dtype=torch.float64, pin_memory=True).numpy()
+A_pin[:] = 1.0
+A_page = np.ones((n, d))
+
+
+def upload(A, tag, **env):
+    for k, v in env.items():
+        os.environ[k] = v
+    for rep in range(2):
+        t0 = time.perf_counter()
+        des = DeviceDesign.from_host(A, b)
+        dt = time.perf_counter() - t0
+        print(f"{tag} rep{rep}: {gb / dt:.1f} GB/s ({dt * 1e3:.0f} ms, copy {des.upload_gram()['copy_ms']:.0f} ms)", flush=True)
+        des.close()
+    for k in env:
+        os.environ.pop(k)
+
+
+upload(A_pin, "pinned source")
+upload(A_page, "pageable, driver staging", FOS_UPLOAD_STAGED="0")
+for t in ("2", "4", "8"):
+    upload(A_page, f"pageable, {t} staging threads", FOS_UPLOAD_THREADS=t)
+os.environ["FOS_UPLOAD_GRAM"] = "1"
+upload(A_page, "pageable, 8 threads + Gram under the copy")
+upload(A_pin, "pinned + Gram under the copy")
