@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -173,8 +175,6 @@ static int design_alloc_work(fos_design* h) {
 // ~380 W, is not capped, and the weighted partition wins: 1520 vs 1443 it/s (kernel 0.592 vs
 // 0.640 ms).  Policy: on when a design joins >= 4 ranks, off otherwise; FOS_BALANCE=1/0 forces it.
 // Without it the blocks are equal and indexed by blockIdx (bit-reproducible across processes).
-#include <map>
-#include <mutex>
 static std::mutex g_bal_mutex;
 static std::map<std::pair<int, int>, std::vector<double>> g_bal_weights;  // (device, n_parts) -> weights
 
@@ -348,6 +348,14 @@ struct HostStager {
         return base ? static_cast<char*>(base) + (static_cast<size_t>(t) * NSLOT + s) * SLOT : nullptr;
     }
 
+    // The pinned slots are shared by the whole process: a stager that has started staging owns
+    // them (this lock) until its last device copy has left them (destructor, after drain()).
+    static std::mutex& slot_owner() {
+        static std::mutex mu;
+        return mu;
+    }
+    std::unique_lock<std::mutex> own;
+
     int device = 0;
     int threads = 8;
     cudaStream_t stream[T] = {};
@@ -403,6 +411,7 @@ struct HostStager {
             FOS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, order_on));
             return FOS_OK;
         }
+        if (!own.owns_lock()) own = std::unique_lock<std::mutex>(slot_owner());
         const size_t pieces = (bytes + SLOT - 1) / SLOT;
         std::atomic<int> err{static_cast<int>(cudaSuccess)};
         auto work = [&](int t) {
