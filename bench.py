@@ -130,9 +130,9 @@ def host_threads():
 def pick_sample_rows(n, d, requested):
     if requested:
         return min(n, requested)
-    # ~2 GB of A: 260 passes (200 for the Lipschitz estimate + 3 per iteration x 20) are
-    # 10-20 s of work for the box's host cores
-    return int(min(n, max(1024, (2 << 30) // (8 * d))))
+    # ~4.3 GB of A: 260 passes (200 for the Lipschitz estimate + 3 per iteration x 20) are
+    # 8-15 s of work for the box's 16 host cores (measured: 3.9-6.4 s at half this size)
+    return int(min(n, max(1024, (4 << 30) // (8 * d))))
 
 
 # ------------------------------------------------------------------------------- main
