@@ -85,6 +85,7 @@ SIGNATURES = {
     "fos_abi_version": (C.c_int, []),
     "fos_last_error": (C.c_char_p, []),
     "fos_device_count": (C.c_int, []),
+    "fos_trim": (C.c_int, []),
     "fos_device_info": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "fos_design_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                     C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),

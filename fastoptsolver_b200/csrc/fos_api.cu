@@ -300,6 +300,11 @@ static void design_free(fos_design* h) {
         }                       \
     } while (0)
 
+// Plain cudaMalloc on purpose.  Once a process has peer access enabled (the exchange windows of a
+// row-sharded design) a FRESH block of this size is also mapped into the peers (measured 200-260 ms
+// for an 8 GB shard with 3 peers, once: the driver then reuses the freed block in 2-25 ms).  The
+// stream-ordered pool (cudaMallocAsync) avoids the peer mapping but pays 300-540 ms for the same
+// 8 GB on EVERY allocation (tools/exp_e2e_multi.py), so it is not used.
 static int alloc_matrix(fos_design* h) {
     const size_t bytes = static_cast<size_t>(h->n) * h->lda * elem_size(h->dtype);
     cudaError_t e = cudaMalloc(&h->A, bytes);
@@ -313,7 +318,6 @@ static int alloc_matrix(fos_design* h) {
     h->owns_b = true;
     return FOS_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------
 // host -> device copies of the design
@@ -332,7 +336,13 @@ struct HostStager {
     static constexpr size_t SLOT = 8u << 20;    // bytes per slot
     static constexpr size_t MIN_BYTES = 128u << 20;  // below this a plain cudaMemcpyAsync is used
 
-    // process-wide pinned slots, allocated on first use and kept (pinning 128 MB costs ~50 ms)
+    static int slot_threads() {
+        int n = 8;
+        if (const char* e = getenv("FOS_UPLOAD_THREADS")) n = std::max(8, std::min(T, atoi(e)));
+        return n;
+    }
+    // process-wide pinned slots (8 threads x 2 x 8 MB = 128 MB unless more threads are asked for at
+    // first use), allocated on first use and kept: pinning them costs ~70 ms
     static void* slots(int t, int s) {
         static std::mutex mu;
         static void* base = nullptr;
@@ -340,13 +350,19 @@ struct HostStager {
         std::lock_guard<std::mutex> lock(mu);
         if (!tried) {
             tried = true;
-            if (cudaMallocHost(&base, static_cast<size_t>(T) * NSLOT * SLOT) != cudaSuccess) {
+            if (cudaMallocHost(&base, static_cast<size_t>(slot_threads()) * NSLOT * SLOT) != cudaSuccess) {
                 cudaGetLastError();
                 base = nullptr;
             }
         }
+        if (base && n_pinned_ref() == 0) n_pinned_ref() = slot_threads();
         return base ? static_cast<char*>(base) + (static_cast<size_t>(t) * NSLOT + s) * SLOT : nullptr;
     }
+    static int& n_pinned_ref() {
+        static int n = 0;
+        return n;
+    }
+    static int pinned_threads() { return n_pinned_ref(); }
 
     // The pinned slots are shared by the whole process: a stager that has started staging owns
     // them (this lock) until its last device copy has left them (destructor, after drain()).
@@ -362,18 +378,27 @@ struct HostStager {
     cudaEvent_t slot_ev[T][NSLOT] = {};
     cudaEvent_t done_ev[T] = {};
     int next_slot[T] = {};
-    bool ready = false;
+    bool ready = false, failed = false;
 
     int init(int dev) {
         device = dev;
+        return FOS_OK;
+    }
+    // streams, events and the pinned slots are created the first time a pageable source shows up
+    // (pinning the slots costs ~0.5 ms per MB: page-locked sources must not pay for it)
+    int prepare() {
+        if (ready || failed) return FOS_OK;
+        failed = true;
         if (slots(0, 0) == nullptr) return FOS_OK;  // no pinned memory: stay on the plain path
         if (const char* e = getenv("FOS_UPLOAD_THREADS")) threads = std::max(1, std::min(T, atoi(e)));
+        threads = std::min(threads, pinned_threads());
         for (int t = 0; t < threads; ++t) {
             FOS_CUDA(cudaStreamCreateWithFlags(&stream[t], cudaStreamNonBlocking));
             FOS_CUDA(cudaEventCreateWithFlags(&done_ev[t], cudaEventDisableTiming));
             for (int q = 0; q < NSLOT; ++q) FOS_CUDA(cudaEventCreateWithFlags(&slot_ev[t][q], cudaEventDisableTiming));
         }
         ready = true;
+        failed = false;
         return FOS_OK;
     }
     void drain() {
@@ -407,7 +432,12 @@ struct HostStager {
     int copy(void* dst, const void* src, size_t bytes, cudaStream_t order_on) {
         const char* e = getenv("FOS_UPLOAD_STAGED");
         const bool force = e && e[0] == '1';
-        if (!ready || (!force && bytes < MIN_BYTES) || !pageable(src)) {
+        bool staged = (force || bytes >= MIN_BYTES) && pageable(src);
+        if (staged) {
+            FOS_TRY(prepare());
+            staged = ready;
+        }
+        if (!staged) {
             FOS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, order_on));
             return FOS_OK;
         }
@@ -454,8 +484,13 @@ static int upload_dense(fos_design* h, const void* A, HostStager& stager, bool w
     FOS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     std::vector<cudaEvent_t> evs;
     cudaEvent_t t_done = nullptr;
+    const bool dbg = getenv("FOS_UPLOAD_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     auto body = [&]() -> int {
+        const auto u0 = now();
         if (with_gram) FOS_TRY(fos_upload_gram_begin(h, cs));
+        const auto u1 = now();
         const size_t row_bytes = static_cast<size_t>(h->lda) * (h->dtype == FOS_F64 ? 8 : 4);
         // 512 MB row chunks in every case: one giant cudaMemcpyAsync pays its whole DMA set-up
         // before the first byte moves (~70 ms for 8 GB), chunks pipeline it
@@ -463,8 +498,10 @@ static int upload_dense(fos_design* h, const void* A, HostStager& stager, bool w
                                           : std::max<long long>(1, (512LL << 20) / static_cast<long long>(row_bytes));
         FOS_CUDA(cudaEventCreate(&t_done));
         FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
-        for (long long r0 = 0; r0 < h->n; r0 += chunk) {
-            const long long rows = std::min<long long>(chunk, h->n - r0);
+        for (long long r0 = 0, rows = 0; r0 < h->n; r0 += rows) {
+            // the last 512 MB go in quarters: the Gram work left after the final byte is one small chunk
+            const long long left = h->n - r0;
+            rows = (with_gram && left <= chunk) ? std::min(left, std::max<long long>(chunk / 4, 1024)) : std::min(chunk, left);
             FOS_TRY(stager.copy(static_cast<char*>(h->A) + static_cast<size_t>(r0) * row_bytes,
                                 static_cast<const char*>(A) + static_cast<size_t>(r0) * row_bytes,
                                 static_cast<size_t>(rows) * row_bytes, h->stream));
@@ -479,10 +516,15 @@ static int upload_dense(fos_design* h, const void* A, HostStager& stager, bool w
         }
         FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
         FOS_CUDA(cudaStreamWaitEvent(cs, h->ev1, 0));
+        const auto u2 = now();
         FOS_TRY(fos_upload_gram_finish(h, cs));  // reduces the splits, synchronises cs
+        const auto u3 = now();
         FOS_CUDA(cudaEventRecord(t_done, cs));
         FOS_CUDA(cudaStreamSynchronize(cs));
         FOS_CUDA(cudaStreamSynchronize(h->stream));
+        if (dbg)
+            fprintf(stderr, "[fos] upload_dense: gram_begin %.1f ms, enqueue loop %.1f ms, finish (sync + free) %.1f ms\n",
+                    ms(u0, u1), ms(u1, u2), ms(u2, u3));
         FOS_CUDA(cudaEventElapsedTime(&h->up_copy_ms, h->ev0, h->ev1));
         FOS_CUDA(cudaEventElapsedTime(&h->up_tail_ms, h->ev1, t_done));
         return FOS_OK;
@@ -511,7 +553,11 @@ extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int6
     const size_t es = elem_size(dtype);
     HostStager stager;
     auto body = [&]() -> int {
+        const auto s0 = std::chrono::steady_clock::now();
         FOS_TRY(stager.init(device));
+        if (getenv("FOS_UPLOAD_DEBUG"))
+            fprintf(stderr, "[fos] stager.init %.1f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count());
         FOS_TRY(stager.copy(h->b, b, static_cast<size_t>(n) * sizeof(double), h->stream));
         if (col_stride == 1 && row_stride >= d) {
             // C order (possibly with a row pitch): strided copy straight into the padded layout

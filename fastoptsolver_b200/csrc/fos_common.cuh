@@ -197,6 +197,7 @@ struct fos_design {
     double* G_up = nullptr;   // [d][d], owned
     int G_state = 0;          // 0 none, 1 local rows, 2 summed over all ranks by the caller
     double* up_W = nullptr;   // split workspace, alive only during the upload
+    size_t up_W_bytes = 0;
     int up_nsplit = 0;
     float up_copy_ms = 0.f, up_tail_ms = 0.f;  // upload duration / Gram work left after the last byte arrived
     // optional per-launch event timing of the gradient kernel

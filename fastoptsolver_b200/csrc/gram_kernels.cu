@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "fos_common.cuh"
 
@@ -460,6 +461,57 @@ static int syrk_pick_split(const fos_design* h, int ntiles, long long rows_avail
     return best;
 }
 
+// Split workspace of the upload-time SYRK (nsplit x d^2 doubles, 0.94 GB at d = 4096): one buffer per
+// device is kept between uploads instead of a cudaMalloc / cudaFree pair per design (the free alone
+// costs 5-35 ms when several processes share the box).  fos_trim() releases it.
+#include <map>
+#include <mutex>
+static std::mutex g_ws_mu;
+static std::map<int, std::pair<void*, size_t>> g_ws_cache;  // device -> (buffer, bytes), not in use
+
+static void* ws_take(int device, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mu);
+        auto it = g_ws_cache.find(device);
+        if (it != g_ws_cache.end()) {
+            void* p = it->second.first;
+            const size_t have = it->second.second;
+            g_ws_cache.erase(it);
+            if (have >= bytes) return p;
+            cudaFree(p);
+        }
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+static void ws_give(int device, void* p, size_t bytes) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mu);
+        if (g_ws_cache.find(device) == g_ws_cache.end()) {
+            g_ws_cache[device] = {p, bytes};
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
+extern "C" int fos_trim(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    for (auto& kv : g_ws_cache) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.first);
+    }
+    g_ws_cache.clear();
+    cudaGetLastError();
+    return FOS_OK;
+}
+
 bool fos_upload_gram_eligible(const fos_design* h) {
     if (h->dtype != FOS_F64 || h->d % GT != 0 || h->d > 4096 || h->lda != h->d) return false;
     const char* e = getenv("FOS_UPLOAD_GRAM");
@@ -486,13 +538,21 @@ int fos_upload_gram_begin(fos_design* h, cudaStream_t s) {
     const int nb = h->d / GT, ntiles = nb * (nb + 1) / 2;
     h->up_nsplit = syrk_pick_split(h, ntiles, fos_upload_gram_chunk_rows(h), d);
     const size_t wbytes = static_cast<size_t>(h->up_nsplit) * d * d * sizeof(double);
-    if (cudaMalloc(&h->up_W, wbytes) != cudaSuccess || cudaMalloc(&h->G_up, d * d * sizeof(double)) != cudaSuccess) {
+    const auto b0 = std::chrono::steady_clock::now();
+    h->up_W = static_cast<double*>(ws_take(h->device, wbytes));
+    h->up_W_bytes = wbytes;
+    if (h->up_W == nullptr || cudaMalloc(&h->G_up, d * d * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         fos_upload_gram_drop(h);
         return FOS_OK;
     }
+    const auto b1 = std::chrono::steady_clock::now();
     FOS_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(syrk_smem_bytes())));
+    if (getenv("FOS_UPLOAD_DEBUG"))
+        fprintf(stderr, "[fos] gram_begin: cudaMalloc(W %.0f MB + G) %.1f ms, func attribute %.1f ms\n", wbytes / 1e6,
+                std::chrono::duration<double, std::milli>(b1 - b0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b1).count());
     FOS_CUDA(cudaMemsetAsync(h->up_W, 0, wbytes, s));
     return FOS_OK;
 }
@@ -522,8 +582,14 @@ int fos_upload_gram_finish(fos_design* h, cudaStream_t s) {
     gram_reduce_kernel<<<dim3(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d)), dim3(256), 0, s>>>(
         h->up_W, h->G_up, d, h->up_nsplit);
     FOS_CUDA(cudaGetLastError());
+    const auto f0 = std::chrono::steady_clock::now();
     FOS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(h->up_W);
+    const auto f1 = std::chrono::steady_clock::now();
+    ws_give(h->device, h->up_W, h->up_W_bytes);
+    if (getenv("FOS_UPLOAD_DEBUG"))
+        fprintf(stderr, "[fos] gram_finish: sync %.1f ms, workspace release %.1f ms\n",
+                std::chrono::duration<double, std::milli>(f1 - f0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - f1).count());
     h->up_W = nullptr;
     h->G_state = 1;
     h->launches += 1;
@@ -531,7 +597,7 @@ int fos_upload_gram_finish(fos_design* h, cudaStream_t s) {
 }
 
 void fos_upload_gram_drop(fos_design* h) {
-    if (h->up_W) cudaFree(h->up_W);
+    if (h->up_W) ws_give(h->device, h->up_W, h->up_W_bytes);
     if (h->G_up) cudaFree(h->G_up);
     h->up_W = nullptr;
     h->G_up = nullptr;

@@ -286,6 +286,12 @@ def find_by_matrix(A, device=0):
     return None
 
 
+def trim():
+    """Release device memory the library keeps between calls (fos_trim: the split workspace of the
+    upload-time Gram accumulation)."""
+    _lib.check(_lib.load().fos_trim())
+
+
 def clear_cache():
     for des, _, _r in _CACHE.values():
         des.close()

@@ -67,6 +67,9 @@ const char* fos_last_error(void);
 int fos_device_count(void);
 /* sm_count, total/free HBM bytes of `device` */
 int fos_device_info(int device, int* sm_count, size_t* total_bytes, size_t* free_bytes);
+/* release device memory the library keeps between calls (the split workspace of the upload-time
+ * Gram accumulation, up to 1.5 GB per device) */
+int fos_trim(void);
 
 /* ---- design: A (n x d) and b (n) resident on one GPU ---------------------------------
  * Replaces the numpy arrays every reference solver takes as (A, b)
