@@ -108,6 +108,9 @@ SIGNATURES = {
     "fos_design_lambda_max": (C.c_int, [C.c_void_p, c_double_p]),
     "fos_comm_window_alloc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fos_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fos_comm_window_alloc_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p]),
+    "fos_comm_attach_fd": (C.c_int, [C.c_void_p, c_int_p, C.c_int]),
+    "fos_comm_window_free": (C.c_int, [C.c_void_p]),
     "fos_comm_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "fos_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, c_double_p]),
     "fos_objective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, c_double_p]),

@@ -285,7 +285,10 @@ static void design_free(fos_design* h) {
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (int r = 0; r < FOS_MAX_WORLD; ++r)
         if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
-    if (h->window) cudaFree(h->window);
+    if (h->vmm)
+        fos_comm_vmm_release(h);
+    else if (h->window)
+        cudaFree(h->window);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -1261,10 +1264,12 @@ extern "C" int fos_comm_attach(fos_design* h, const void* ipc_handles, int world
         h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
     }
     h->world = world;
-    {
-        const char* e = getenv("FOS_BALANCE");
-        if (world >= 4 && !(e && e[0] == '0') && !h->balanced) FOS_TRY(fos_balance_rows(h));
-    }
+    return fos_comm_after_attach(h);
+}
+
+int fos_comm_after_attach(fos_design* h) {
+    const char* e = getenv("FOS_BALANCE");
+    if (h->world >= 4 && !(e && e[0] == '0') && !h->balanced) FOS_TRY(fos_balance_rows(h));
     return FOS_OK;
 }
 

@@ -179,6 +179,12 @@ struct fos_design {
     void* window = nullptr;        // this rank's exchange window (cudaMalloc, IPC-exported)
     size_t window_bytes = 0;
     void* peer_base[8] = {nullptr};  // cudaIpcOpenMemHandle results (to close on destroy)
+    // windows shared through the virtual-memory-management API instead (comm_vmm.cu)
+    bool vmm = false;
+    unsigned long long vmm_handle[8] = {0};  // CUmemGenericAllocationHandle per rank (own + imported)
+    void* vmm_ptr[8] = {nullptr};            // where each rank's window is mapped in this process
+    size_t vmm_size = 0, vmm_gran = 0;
+    int vmm_fd = -1;                         // exported descriptor of the own window
     FosPeer peer{};
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
@@ -219,6 +225,8 @@ int fos_launch_grad(fos_design* h, int mode_override);
 int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hist, double a1,
                         double a2, int bits);
 int fos_grad_plan(fos_design* h);
+void fos_comm_vmm_release(fos_design* h);
+int fos_comm_after_attach(fos_design* h);  // common tail of the attach variants (row-balance policy)
 int fos_balance_rows(fos_design* h);  // SM-indexed row partition weighted by measured per-SM rates  // picks kernel + n_parts, sets smem attributes
 int fos_launch_prox(const double* v_dev, double* out_dev, long long len, double thresh,
                     double scale, cudaStream_t stream);

@@ -37,12 +37,102 @@ def exchange_bytes(payload: bytes, dist, group=None):
     return out
 
 
+def exchange_fds(my_fd: int, dist, group=None, timeout=60.0):
+    """Hand one file descriptor per rank to every other rank of the box (unix socket in the abstract
+    namespace, SCM_RIGHTS).  Returns a list with, for every peer rank, a descriptor valid in THIS
+    process (own entry -1); the caller closes them."""
+    import os
+    import socket
+    import threading
+    import uuid
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    name = f"\0fos-b200-{os.getpid()}-{uuid.uuid4().hex}"
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.settimeout(timeout)
+    srv.bind(name)
+    srv.listen(world)
+    names = [None] * world
+    dist.all_gather_object(names, name, group=group)
+    errors = []
+
+    def serve():
+        try:
+            for _ in range(world - 1):
+                conn, _addr = srv.accept()
+                with conn:
+                    socket.send_fds(conn, [b"w"], [my_fd])
+        except Exception as e:  # reported by the receiving side as a missing descriptor
+            errors.append(e)
+
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    fds = [-1] * world
+    try:
+        for r in range(world):
+            if r == rank:
+                continue
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                c.settimeout(timeout)
+                c.connect(names[r])
+                _msg, got, _flags, _addr = socket.recv_fds(c, 16, 1)
+                if not got:
+                    raise RuntimeError(f"rank {r} sent no descriptor")
+                fds[r] = got[0]
+    finally:
+        t.join(timeout)
+        srv.close()
+    if errors:
+        raise RuntimeError(f"could not hand the window descriptor to every peer: {errors[0]}")
+    return fds
+
+
+def _all_ok(ok: bool, dist, group):
+    flags = [None] * dist.get_world_size(group)
+    dist.all_gather_object(flags, bool(ok), group=group)
+    return all(flags)
+
+
+def _attach_vmm(des, dist, group):
+    """Windows as cuMemCreate allocations shared by file descriptor (include/fos.h,
+    fos_comm_window_alloc_fd).  Returns False -- with nothing left behind on any rank -- if some
+    rank cannot do it; the caller then falls back to the cudaIpc windows."""
+    import os
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    fd = C.c_int(-1)
+    ok = lib.fos_comm_window_alloc_fd(des.handle, rank, world, C.byref(fd)) == _lib.FOS_OK
+    if not _all_ok(ok, dist, group):
+        if ok:
+            _lib.check(lib.fos_comm_window_free(des.handle))
+        return False
+    fds, err = [-1] * world, None
+    try:
+        fds = exchange_fds(fd.value, dist, group)
+        arr = (C.c_int * world)(*fds)
+        ok = lib.fos_comm_attach_fd(des.handle, arr, world) == _lib.FOS_OK
+    except Exception as e:      # socket trouble: treated like an import failure
+        ok, err = False, e
+    finally:
+        for f in fds:
+            if f >= 0:
+                os.close(f)
+    if not _all_ok(ok, dist, group):
+        # some rank could not import: nobody has signalled a peer yet, so the windows can go
+        raise RuntimeError("sharing the exchange windows by file descriptor failed half-way"
+                           + (f": {err}" if err else "") + "; set FOS_COMM=ipc to use cudaIpc windows")
+    return True
+
+
 def attach(des: DeviceDesign, dist, group=None):
-    """Allocate this rank's exchange window, swap IPC handles, map the peers."""
+    """Allocate this rank's exchange window, hand it to the peers, map theirs."""
+    import os
     lib = _lib.load()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world > 8:
         raise ValueError("at most 8 ranks (one NVSwitch box) are supported")
+    if os.environ.get("FOS_COMM", "vmm") != "ipc" and _attach_vmm(des, dist, group):
+        dist.barrier(group)      # nobody signals a peer before every window is mapped
+        return group
     buf = C.create_string_buffer(64)
     _lib.check(lib.fos_comm_window_alloc(des.handle, rank, world, buf))
     handles = exchange_bytes(buf.raw, dist, group)

@@ -137,6 +137,18 @@ int fos_design_lambda_max(fos_design* h, double* out);
 int fos_comm_window_alloc(fos_design* h, int rank, int world, void* ipc_handle_out64);
 int fos_comm_attach(fos_design* h, const void* ipc_handles /* world x 64 bytes */, int world);
 int fos_comm_info(const fos_design* h, int* rank, int* world);
+/* Preferred variant: the window is a cuMemCreate allocation exported as a POSIX file descriptor
+ * (*fd_out, owned by the design); the caller passes the descriptors around (unix socket,
+ * SCM_RIGHTS) and hands fos_comm_attach_fd the ones it RECEIVED (fds[r] = rank r's window as a
+ * descriptor valid in this process; own entry ignored; the caller closes them afterwards).  A peer
+ * maps the window for its own device only, so -- unlike cudaIpcOpenMemHandle, which enables peer
+ * access for the device pair and makes every later cudaMalloc of the process peer-visible (200-260
+ * ms for a fresh 8 GB block with 3 peers) -- nothing else is affected.  FOS_ERR_UNSUPPORTED: use
+ * the cudaIpc pair above. */
+int fos_comm_window_alloc_fd(fos_design* h, int rank, int world, int* fd_out);
+int fos_comm_attach_fd(fos_design* h, const int* fds, int world);
+/* drop a window that has not been attached yet (either kind), e.g. to fall back to the other variant */
+int fos_comm_window_free(fos_design* h);
 
 /* ---- one-shot operators ----------------------------------------------------------------
  * fos_grad: loss = 0.5||Ax-b||^2 (+0.5 a2 ||x||^2), g = A^T(Ax-b) (+a2 x), A read ONCE.

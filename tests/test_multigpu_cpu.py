@@ -33,6 +33,21 @@ def _worker(rank, world, port, q):
         mine = bytes([rank]) * 64
         got = multigpu.exchange_bytes(mine, dist)
         assert got == [bytes([r]) * 64 for r in range(world)]
+        # 1b. descriptor exchange (the transport of the VMM exchange windows): every rank hands out
+        # the read end of a pipe it keeps writing to; the descriptors received from the peers must
+        # be live duplicates in this process
+        rd, wr = os.pipe()
+        fds = multigpu.exchange_fds(rd, dist)
+        assert fds[rank] == -1 and all(f >= 0 for r, f in enumerate(fds) if r != rank)
+        os.write(wr, bytes([65 + rank]) * (world - 1))       # one byte for every peer to read
+        dist.barrier()
+        for r, f in enumerate(fds):
+            if r != rank:
+                assert os.read(f, 1) == bytes([65 + r])
+                os.close(f)
+        os.close(rd)
+        os.close(wr)
+        assert multigpu._all_ok(True, dist, None) and not multigpu._all_ok(rank == 0, dist, None)
         # 2. sharded gradient algebra on an uneven split
         rng = np.random.default_rng(0)
         n, d = 1001, 17
