@@ -124,27 +124,42 @@ static int design_common_init(fos_design* h, long long n, long long d, int dtype
 
 static int design_alloc_work(fos_design* h) {
     FOS_TRY(fos_grad_plan(h));
+    // ONE device block and ONE pinned block for all per-design workspaces: every separate
+    // cudaMalloc / cudaMallocHost is a trip through the driver's global lock (50 ms for the lot when
+    // eight ranks create their designs at the same moment)
     const size_t vb = static_cast<size_t>(h->ldv) * sizeof(double);
-    FOS_CUDA(cudaMalloc(&h->partial_g, static_cast<size_t>(h->n_parts) * vb));
-    FOS_CUDA(cudaMalloc(&h->partial_s, static_cast<size_t>(h->n_parts) * 2 * sizeof(double)));
-    FOS_CUDA(cudaMemsetAsync(h->partial_g, 0, static_cast<size_t>(h->n_parts) * vb, h->stream));
-    FOS_CUDA(cudaMemsetAsync(h->partial_s, 0, static_cast<size_t>(h->n_parts) * 2 * sizeof(double), h->stream));
-    double** vecs[4] = {&h->y, &h->xc, &h->xk, &h->g};
-    for (auto v : vecs) {
-        FOS_CUDA(cudaMalloc(v, vb));
-        FOS_CUDA(cudaMemsetAsync(*v, 0, vb, h->stream));
-    }
+    auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    const size_t o_pg = 0;
+    const size_t o_ps = o_pg + up(static_cast<size_t>(h->n_parts) * vb);
+    const size_t o_y = o_ps + up(static_cast<size_t>(h->n_parts) * 2 * sizeof(double));
+    const size_t o_xc = o_y + up(vb), o_xk = o_xc + up(vb), o_g = o_xk + up(vb);
+    const size_t o_row = o_g + up(vb);
+    const size_t o_ctrl = o_row + up((h->n_parts + 1) * sizeof(long long));
+    const size_t total = o_ctrl + up(sizeof(FosCtrl));
+    FOS_CUDA(cudaMalloc(&h->work_block, total));
+    FOS_CUDA(cudaMemsetAsync(h->work_block, 0, total, h->stream));
+    char* wb = static_cast<char*>(h->work_block);
+    h->partial_g = reinterpret_cast<double*>(wb + o_pg);
+    h->partial_s = reinterpret_cast<double*>(wb + o_ps);
+    h->y = reinterpret_cast<double*>(wb + o_y);
+    h->xc = reinterpret_cast<double*>(wb + o_xc);
+    h->xk = reinterpret_cast<double*>(wb + o_xk);
+    h->g = reinterpret_cast<double*>(wb + o_g);
+    h->row_lo = reinterpret_cast<long long*>(wb + o_row);
+    h->ctrl = reinterpret_cast<FosCtrl*>(wb + o_ctrl);
     // row partition of the streaming kernel: equal blocks to start with
     h->row_lo_host.resize(h->n_parts + 1);
     for (int c = 0; c <= h->n_parts; ++c) h->row_lo_host[c] = (h->n * c) / h->n_parts;
-    FOS_CUDA(cudaMalloc(&h->row_lo, (h->n_parts + 1) * sizeof(long long)));
     FOS_CUDA(cudaMemcpyAsync(h->row_lo, h->row_lo_host.data(), (h->n_parts + 1) * sizeof(long long),
                              cudaMemcpyHostToDevice, h->stream));
-    FOS_CUDA(cudaMalloc(&h->ctrl, sizeof(FosCtrl)));
-    FOS_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(FosCtrl), h->stream));
-    FOS_CUDA(cudaMallocHost(&h->ctrl_host, 4 * sizeof(FosCtrl)));
-    FOS_CUDA(cudaMallocHost(&h->vec_host, (2 * static_cast<size_t>(h->ldv) + 16) * sizeof(double)));
-    FOS_CUDA(cudaMallocHost(&h->pin_scratch, FOS_PIN_SCRATCH));
+    const size_t p_ctrl = 0;
+    const size_t p_vec = p_ctrl + up(4 * sizeof(FosCtrl));
+    const size_t p_scr = p_vec + up((2 * static_cast<size_t>(h->ldv) + 16) * sizeof(double));
+    FOS_CUDA(cudaMallocHost(&h->pin_block, p_scr + FOS_PIN_SCRATCH));
+    char* pb = static_cast<char*>(h->pin_block);
+    h->ctrl_host = reinterpret_cast<FosCtrl*>(pb + p_ctrl);
+    h->vec_host = reinterpret_cast<double*>(pb + p_vec);
+    h->pin_scratch = pb + p_scr;
     memset(h->ctrl_host, 0, 4 * sizeof(FosCtrl));
     FOS_CUDA(cudaStreamSynchronize(h->stream));
     {
@@ -274,12 +289,10 @@ static void design_free(fos_design* h) {
     if (h->owns_A && h->A) cudaFree(h->A);
     if (h->owns_b && h->b) cudaFree(h->b);
     fos_upload_gram_drop(h);
-    void* bufs[] = {h->partial_g, h->partial_s, h->y, h->xc, h->xk, h->g, h->ctrl, h->row_lo, h->sm_slot, h->arena};
+    void* bufs[] = {h->work_block, h->sm_slot, h->arena};
     for (void* p : bufs)
         if (p) cudaFree(p);
-    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
-    if (h->vec_host) cudaFreeHost(h->vec_host);
-    if (h->pin_scratch) cudaFreeHost(h->pin_scratch);
+    if (h->pin_block) cudaFreeHost(h->pin_block);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -690,7 +703,7 @@ extern "C" int fos_design_upload_gram(fos_design* h, double** G_dev, int* state,
 
 extern "C" int fos_design_upload_gram_set(fos_design* h, int state) {
     FOS_REQUIRE(h, "null design");
-    FOS_REQUIRE(state == 0 || state == 2, "state must be 0 (discard) or 2 (summed over all ranks)");
+    FOS_REQUIRE(state == 0 || state == 2, "state must be 0 (discard) or 2 (held by every rank)");
     if (state == 0) {
         FOS_CUDA(cudaSetDevice(h->device));
         fos_upload_gram_drop(h);
@@ -964,8 +977,9 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     FOS_REQUIRE(h && v0 && L_out, "null pointer argument");
     FOS_REQUIRE(n_iter >= 1, "n_iter must be >= 1");
     FOS_CUDA(cudaSetDevice(h->device));
-    // a Gram matrix accumulated under the upload (summed over the ranks if the rows are sharded):
-    // iterate on it instead of streaming A twice a hundred times
+    // a Gram matrix accumulated under the upload: iterate on it instead of streaming A twice a
+    // hundred times
+    // (row-sharded ranks: state 2 = every rank confirmed it holds the matrix of its own rows)
     if (h->G_up && ((h->world == 1 && h->G_state == 1) || (h->world > 1 && h->G_state == 2)))
         return fos_gram_power_iter(h, v0, n_iter, tol, L_out, iters_out, gpu_ms_out);
     FosCtrl* c = h->ctrl_host;

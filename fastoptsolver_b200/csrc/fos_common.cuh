@@ -164,7 +164,9 @@ struct fos_design {
     void* A = nullptr;
     double* b = nullptr;
     bool owns_A = false, owns_b = false;
-    // workspaces
+    // workspaces (carved out of work_block / pin_block)
+    void* work_block = nullptr;
+    void* pin_block = nullptr;
     int n_parts = 0;
     double* partial_g = nullptr;
     double* partial_s = nullptr;

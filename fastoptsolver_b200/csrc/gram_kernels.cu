@@ -356,9 +356,12 @@ struct GramPowerState {
     int pit, pit_max, done, pad;
 };
 
+// `st` (one GPU: finish kernel below) or `ctrl` (row-sharded ranks: the epilogue kernel's EOP_POWER
+// step follows, which adds the ranks' products through the exchange windows) says when to stop.
 __global__ void __launch_bounds__(256) gram_matvec_kernel(const double* __restrict__ G, const double* __restrict__ v,
-                                                          double* __restrict__ w, int d, const GramPowerState* st) {
-    if (st->done) return;
+                                                          double* __restrict__ w, int d, const GramPowerState* st,
+                                                          const FosCtrl* ctrl) {
+    if (st ? st->done : (ctrl->g_mode == GM_SKIP)) return;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= d) return;
     const double2* g2 = reinterpret_cast<const double2*>(G + static_cast<size_t>(row) * d);
@@ -604,8 +607,62 @@ void fos_upload_gram_drop(fos_design* h) {
     h->G_state = 0;
 }
 
+// Row-sharded ranks: every rank holds the Gram matrix of ITS rows, so A^T A v = sum_r G_r v.  Each
+// step is a local product followed by the epilogue kernel's power-iteration step (EOP_POWER) with
+// the product standing in as the single "partial" row: that step sums the ranks' vectors in rank
+// order through the exchange windows (the same fused all-reduce as every streaming pass: 32 KB,
+// no library collective, bit-identical L on all ranks), normalises and applies the stop test.
+static int gram_power_iter_sharded(fos_design* h, const double* v0, int n_iter, double tol, double* L_out,
+                                   int* iters_out, float* gpu_ms_out) {
+    const int d = h->d;
+    void* base = nullptr;
+    FOS_TRY(fos_arena_reserve(h, static_cast<size_t>(h->ldv) * sizeof(double), &base));
+    double* w = static_cast<double*>(base);
+    FosCtrl* c = h->ctrl_host;
+    memset(c, 0, sizeof(FosCtrl));
+    c->g_mode = GM_GRAD | GM_NOB;
+    c->phase = PH_DONE;
+    c->ptol = tol;
+    c->pit_max = n_iter;
+    FOS_CUDA(cudaMemcpyAsync(h->ctrl, c, sizeof(FosCtrl), cudaMemcpyHostToDevice, h->stream));
+    memcpy(h->vec_host, v0, static_cast<size_t>(d) * sizeof(double));
+    for (int q = d; q < h->ldv; ++q) h->vec_host[q] = 0.0;
+    FOS_CUDA(cudaMemcpyAsync(h->y, h->vec_host, static_cast<size_t>(h->ldv) * sizeof(double), cudaMemcpyHostToDevice,
+                             h->stream));
+    FOS_CUDA(cudaMemsetAsync(w, 0, static_cast<size_t>(h->ldv) * sizeof(double), h->stream));
+    FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    // the epilogue reads its partial rows from the design: point it at the product for this loop
+    double* saved_pg = h->partial_g;
+    const int saved_np = h->n_parts;
+    h->partial_g = w;
+    h->n_parts = 1;
+    FosHist none{};
+    int status = FOS_OK;
+    for (int k = 0; k < n_iter && status == FOS_OK; ++k) {
+        gram_matvec_kernel<<<dim3((d + 7) / 8), dim3(256), 0, h->stream>>>(h->G_up, h->y, w, d, nullptr, h->ctrl);
+        h->launches += 1;
+        status = fos_launch_epilogue(h, EOP_POWER, 0, none, 0.0, 0.0, 0);
+    }
+    h->partial_g = saved_pg;
+    h->n_parts = saved_np;
+    FOS_TRY(status);
+    FOS_CUDA(cudaGetLastError());
+    FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    FOS_CUDA(cudaMemcpyAsync(c, h->ctrl, sizeof(FosCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    if (c->stop_reason < 0) {
+        fos_set_error("multi-GPU exchange timed out: a peer rank never arrived");
+        return FOS_ERR_COMM;
+    }
+    *L_out = c->L;
+    if (iters_out) *iters_out = c->pit;
+    if (gpu_ms_out) FOS_CUDA(cudaEventElapsedTime(gpu_ms_out, h->ev0, h->ev1));
+    return FOS_OK;
+}
+
 int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol, double* L_out, int* iters_out,
                         float* gpu_ms_out) {
+    if (h->world > 1) return gram_power_iter_sharded(h, v0, n_iter, tol, L_out, iters_out, gpu_ms_out);
     const int d = h->d;
     void* base = nullptr;
     FOS_TRY(fos_arena_reserve(h, 256 + static_cast<size_t>(d) * sizeof(double), &base));
@@ -623,7 +680,7 @@ int fos_gram_power_iter(fos_design* h, const double* v0, int n_iter, double tol,
                                  h->stream));
         FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
         for (int k = 0; k < n_iter; ++k) {
-            gram_matvec_kernel<<<dim3((d + 7) / 8), dim3(256), 0, h->stream>>>(h->G_up, h->y, w, d, st);
+            gram_matvec_kernel<<<dim3((d + 7) / 8), dim3(256), 0, h->stream>>>(h->G_up, h->y, w, d, st, nullptr);
             gram_power_finish_kernel<<<dim3(1), dim3(1024), 0, h->stream>>>(w, h->y, d, st);
         }
         FOS_CUDA(cudaGetLastError());
@@ -663,7 +720,7 @@ extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
         g->bb = 2.0 * half_bb;
         FOS_CUDA(cudaMemcpy(g->c, gneg.data(), static_cast<size_t>(d) * sizeof(double), cudaMemcpyHostToDevice));
 
-        if (h->G_up && h->G_state == 1) {
+        if (h->G_up && h->G_state >= 1) {
             // already accumulated under the upload of this design: copy instead of rebuilding
             cudaEventRecord(g->ev0, g->stream);
             FOS_CUDA(cudaMemcpyAsync(g->G, h->G_up, static_cast<size_t>(d) * d * sizeof(double), cudaMemcpyDeviceToDevice,

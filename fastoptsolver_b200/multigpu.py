@@ -37,109 +37,167 @@ def exchange_bytes(payload: bytes, dist, group=None):
     return out
 
 
-def exchange_fds(my_fd: int, dist, group=None, timeout=60.0):
-    """Hand one file descriptor per rank to every other rank of the box (unix socket in the abstract
-    namespace, SCM_RIGHTS).  Returns a list with, for every peer rank, a descriptor valid in THIS
-    process (own entry -1); the caller closes them."""
-    import os
-    import socket
-    import threading
-    import uuid
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    name = f"\0fos-b200-{os.getpid()}-{uuid.uuid4().hex}"
-    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    srv.settimeout(timeout)
-    srv.bind(name)
-    srv.listen(world)
-    names = [None] * world
-    dist.all_gather_object(names, name, group=group)
-    errors = []
-
-    def serve():
-        try:
-            for _ in range(world - 1):
-                conn, _addr = srv.accept()
-                with conn:
-                    socket.send_fds(conn, [b"w"], [my_fd])
-        except Exception as e:  # reported by the receiving side as a missing descriptor
-            errors.append(e)
-
-    t = threading.Thread(target=serve, daemon=True)
-    t.start()
-    fds = [-1] * world
-    try:
-        for r in range(world):
-            if r == rank:
-                continue
-            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
-                c.settimeout(timeout)
-                c.connect(names[r])
-                _msg, got, _flags, _addr = socket.recv_fds(c, 16, 1)
-                if not got:
-                    raise RuntimeError(f"rank {r} sent no descriptor")
-                fds[r] = got[0]
-    finally:
-        t.join(timeout)
-        srv.close()
-    if errors:
-        raise RuntimeError(f"could not hand the window descriptor to every peer: {errors[0]}")
-    return fds
+def _gather(obj, dist, group):
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
 
 
 def _all_ok(ok: bool, dist, group):
-    flags = [None] * dist.get_world_size(group)
-    dist.all_gather_object(flags, bool(ok), group=group)
-    return all(flags)
+    return all(_gather(bool(ok), dist, group))
 
 
-def _attach_vmm(des, dist, group):
-    """Windows as cuMemCreate allocations shared by file descriptor (include/fos.h,
-    fos_comm_window_alloc_fd).  Returns False -- with nothing left behind on any rank -- if some
-    rank cannot do it; the caller then falls back to the cudaIpc windows."""
-    import os
-    lib = _lib.load()
+class _FdServer:
+    """Hands this rank's descriptor to every peer that connects (unix socket in the abstract
+    namespace, SCM_RIGHTS)."""
+
+    def __init__(self, world, timeout=60.0):
+        import os
+        import socket
+        import uuid
+        self.world, self.timeout = world, timeout
+        self.name = f"\0fos-b200-{os.getpid()}-{uuid.uuid4().hex}"
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self.sock.settimeout(timeout)
+        self.sock.bind(self.name)
+        self.sock.listen(world)
+        self.errors = []
+        self.thread = None
+
+    def serve(self, fd):
+        import socket
+        import threading
+
+        def run():
+            try:
+                for _ in range(self.world - 1):
+                    conn, _addr = self.sock.accept()
+                    with conn:
+                        socket.send_fds(conn, [b"w"], [fd])
+            except Exception as e:      # the receiving side reports the missing descriptor
+                self.errors.append(e)
+
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+
+    def close(self):
+        if self.thread is not None:
+            self.thread.join(self.timeout)
+        self.sock.close()
+
+
+def _receive_fds(names, rank, timeout=60.0):
+    import socket
+    fds = [-1] * len(names)
+    for r, name in enumerate(names):
+        if r == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+            c.settimeout(timeout)
+            c.connect(name)
+            _msg, got, _flags, _addr = socket.recv_fds(c, 16, 1)
+            if not got:
+                raise RuntimeError(f"rank {r} sent no descriptor")
+            fds[r] = got[0]
+    return fds
+
+
+def exchange_fds(my_fd: int, dist, group=None, timeout=60.0):
+    """Hand one file descriptor per rank to every other rank of the box.  Returns a list with, for
+    every peer rank, a descriptor valid in THIS process (own entry -1); the caller closes them."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    fd = C.c_int(-1)
-    ok = lib.fos_comm_window_alloc_fd(des.handle, rank, world, C.byref(fd)) == _lib.FOS_OK
-    if not _all_ok(ok, dist, group):
-        if ok:
-            _lib.check(lib.fos_comm_window_free(des.handle))
-        return False
-    fds, err = [-1] * world, None
+    srv = _FdServer(world, timeout)
     try:
-        fds = exchange_fds(fd.value, dist, group)
-        arr = (C.c_int * world)(*fds)
-        ok = lib.fos_comm_attach_fd(des.handle, arr, world) == _lib.FOS_OK
-    except Exception as e:      # socket trouble: treated like an import failure
-        ok, err = False, e
+        names = _gather(srv.name, dist, group)
+        srv.serve(my_fd)
+        fds = _receive_fds(names, rank, timeout)
     finally:
-        for f in fds:
-            if f >= 0:
-                os.close(f)
-    if not _all_ok(ok, dist, group):
-        # some rank could not import: nobody has signalled a peer yet, so the windows can go
-        raise RuntimeError("sharing the exchange windows by file descriptor failed half-way"
-                           + (f": {err}" if err else "") + "; set FOS_COMM=ipc to use cudaIpc windows")
-    return True
+        srv.close()
+    if srv.errors:
+        raise RuntimeError(f"could not hand the descriptor to every peer: {srv.errors[0]}")
+    return fds
 
 
-def attach(des: DeviceDesign, dist, group=None):
-    """Allocate this rank's exchange window, hand it to the peers, map theirs."""
+def share_windows(alloc_fd, attach_fd, free_window, alloc_ipc, attach_ipc, dist, group=None, piggyback=None,
+                  prefer_vmm=True):
+    """The collective part of wiring the exchange windows, independent of the library calls (which
+    are passed in, so that the CPU tests can drive it with stand-ins):
+
+      alloc_fd()        -> descriptor of this rank's VMM window, or None if unsupported here
+      attach_fd(fds)    -> True once the peers' windows (descriptors valid in this process) are mapped
+      free_window()     -> drop a window that was allocated but is not attached
+      alloc_ipc()       -> 64-byte cudaIpc handle of a freshly allocated window
+      attach_ipc(blobs) -> map the peers' windows from their handles
+
+    Two object all-gathers in total: (VMM ok?, socket name) before and (attached ok?, piggyback)
+    after; the second doubles as the barrier "nobody signals a peer before every window is mapped".
+    Returns (kind, [piggyback of every rank])."""
+    import os
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if prefer_vmm:
+        srv = _FdServer(world)
+        fds = [-1] * world
+        try:
+            fd = alloc_fd()
+            first = _gather((fd is not None, srv.name), dist, group)
+            if all(ok for ok, _ in first):
+                ok, err = True, None
+                try:
+                    srv.serve(fd)
+                    fds = _receive_fds([name for _, name in first], rank)
+                    ok = bool(attach_fd(fds))
+                except Exception as e:      # socket trouble counts like an import failure
+                    ok, err = False, e
+                second = _gather((ok and not srv.errors, piggyback), dist, group)
+                if not all(ok for ok, _ in second):
+                    raise RuntimeError("sharing the exchange windows by file descriptor failed half-way"
+                                       + (f": {err}" if err else "") + "; set FOS_COMM=ipc to use cudaIpc windows")
+                return "vmm", [p for _, p in second]
+            if fd is not None:
+                free_window()
+        finally:
+            srv.close()
+            for f in fds:
+                if f >= 0:
+                    os.close(f)
+    handles = _gather(alloc_ipc(), dist, group)
+    if any(len(hd) != 64 for hd in handles):
+        raise RuntimeError("ranks published handles of different sizes")
+    attach_ipc(handles)
+    return "ipc", _gather(piggyback, dist, group)
+
+
+def attach(des: DeviceDesign, dist, group=None, piggyback=None):
+    """Allocate this rank's exchange window, hand it to the peers, map theirs.  Returns the
+    ``piggyback`` objects of all ranks (they ride on the closing all-gather)."""
     import os
     lib = _lib.load()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world > 8:
         raise ValueError("at most 8 ranks (one NVSwitch box) are supported")
-    if os.environ.get("FOS_COMM", "vmm") != "ipc" and _attach_vmm(des, dist, group):
-        dist.barrier(group)      # nobody signals a peer before every window is mapped
-        return group
-    buf = C.create_string_buffer(64)
-    _lib.check(lib.fos_comm_window_alloc(des.handle, rank, world, buf))
-    handles = exchange_bytes(buf.raw, dist, group)
-    blob = C.create_string_buffer(b"".join(handles), 64 * world)
-    _lib.check(lib.fos_comm_attach(des.handle, blob, world))
-    dist.barrier(group)          # nobody signals a peer before every window is mapped
-    return group
+
+    def alloc_fd():
+        fd = C.c_int(-1)
+        ok = lib.fos_comm_window_alloc_fd(des.handle, rank, world, C.byref(fd)) == _lib.FOS_OK
+        return fd.value if ok else None
+
+    def attach_fd(fds):
+        return lib.fos_comm_attach_fd(des.handle, (C.c_int * world)(*fds), world) == _lib.FOS_OK
+
+    def alloc_ipc():
+        buf = C.create_string_buffer(64)
+        _lib.check(lib.fos_comm_window_alloc(des.handle, rank, world, buf))
+        return buf.raw
+
+    def attach_ipc(handles):
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        _lib.check(lib.fos_comm_attach(des.handle, blob, world))
+
+    kind, extras = share_windows(alloc_fd, attach_fd, lambda: _lib.check(lib.fos_comm_window_free(des.handle)),
+                                 alloc_ipc, attach_ipc, dist, group, piggyback,
+                                 prefer_vmm=os.environ.get("FOS_COMM", "vmm") != "ipc")
+    des.comm_kind = kind
+    return extras
 
 
 def sharded_from_host(A_local, b_local, dist, group=None, device=None):
@@ -149,38 +207,18 @@ def sharded_from_host(A_local, b_local, dist, group=None, device=None):
         import torch
         device = torch.cuda.current_device()
     des = DeviceDesign.from_host(A_local, b_local, device=device)
-    attach(des, dist, group)
-    allreduce_upload_gram(des, dist, group)
+    # Every rank accumulated the Gram matrix of its own rows under the upload (include/fos.h,
+    # fos_design_upload_gram)?  Then estimate_lipschitz iterates on them -- local product, then the
+    # same fused peer-memory all-reduce of the d-vector as a streaming pass; the matrices are never
+    # summed.  All ranks must take the same branch: if any rank has none (shard below the size
+    # threshold, workspace allocation failed), all discard theirs and keep streaming.
+    have = des.upload_gram()["state"] == 1
+    everyone = attach(des, dist, group, piggyback=have)
+    if all(everyone):
+        des.set_upload_gram(2)
+    elif have:
+        des.set_upload_gram(0)
     return des
-
-
-def allreduce_upload_gram(des: DeviceDesign, dist, group=None):
-    """If every rank accumulated the Gram matrix of its rows under the upload (include/fos.h,
-    fos_design_upload_gram), sum them over the ranks in place -- d^2 doubles, once, a plain library
-    all-reduce -- so that ``estimate_lipschitz`` iterates on G instead of streaming A; if any
-    rank has none, all ranks discard theirs and keep the streaming power iteration."""
-    import torch
-    info = des.upload_gram()
-    if "nccl" not in str(dist.get_backend(group)):
-        # no device collective on this group (same answer on every rank): keep streaming
-        if info["state"] != 0:
-            des.set_upload_gram(0)
-        return False
-    dev = f"cuda:{des.device}"
-    flag = torch.tensor([1 if info["state"] == 1 else 0], device=dev, dtype=torch.int32)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag.item()) == 0:
-        if info["state"] != 0:
-            des.set_upload_gram(0)
-        return False
-    d = des.shape[1]
-    arr = type("_G", (), {"__cuda_array_interface__": {"shape": (d, d), "typestr": "<f8", "data": (int(info["ptr"]), False),
-                                                       "version": 3, "strides": None}})()
-    G = torch.as_tensor(arr, device=dev)
-    dist.all_reduce(G, group=group)
-    torch.cuda.synchronize(G.device)
-    des.set_upload_gram(2)
-    return True
 
 
 def sharded_synthetic(n_total, d, dist, group=None, device=None, dtype=np.float64, **scenario):

@@ -104,9 +104,13 @@ int fos_design_pointers(fos_design* h, void** A_dev, double** b_dev);
  * the last byte.  fos_power_iter (estimate_lipschitz, iterative_solvers.py:45-60) then iterates
  * w = G v instead of w = A^T(A v): the same numbers up to rounding (relative 1e-15 on L), 100 x
  * d^2 instead of 100 x n d doubles of traffic.  fos_gram_create reuses the matrix as well.
- * state: 0 none, 1 local rows, 2 summed over all ranks.  Row-sharded callers all-reduce *G_dev
- * in place and then call fos_design_upload_gram_set(h, 2); until then sharded designs keep the
- * streaming power iteration.  fos_design_upload_gram_set(h, 0) discards the matrix. */
+ * state: 0 none, 1 local rows, 2 local rows and confirmed on every rank.  Row-sharded designs
+ * never sum the matrices: A^T A v = sum_r G_r v, so each step is a local product whose result goes
+ * through the same fused peer-memory all-reduce as a streaming pass (32 KB per step).  All ranks
+ * must take the same branch, so the caller first agrees that EVERY rank holds its matrix and then
+ * calls fos_design_upload_gram_set(h, 2) (else (h, 0) on all ranks, which discards it); until then
+ * a sharded design keeps the streaming power iteration.  fos_gram_create copies the local matrix
+ * in either state (its caller sums the copies). */
 int fos_design_upload_gram(fos_design* h, double** G_dev, int* state, float* copy_ms, float* tail_ms);
 int fos_design_upload_gram_set(fos_design* h, int state);
 /* Column statistics of the resident design (one pass over A): out[c] = sum_i (A[i][c] - center[c])^p

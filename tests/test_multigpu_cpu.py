@@ -48,6 +48,45 @@ def _worker(rank, world, port, q):
         os.close(rd)
         os.close(wr)
         assert multigpu._all_ok(True, dist, None) and not multigpu._all_ok(rank == 0, dist, None)
+        # 1c. the collective logic of wiring the exchange windows, driven with stand-ins for the
+        # library calls: descriptor route, fall-back to the handle route when one rank cannot do
+        # descriptors (the others must drop their windows), forced handle route; the piggy-backed
+        # objects of all ranks come back in rank order
+        log = []
+
+        def make(vmm_ok):
+            pipe = os.pipe()
+            os.write(pipe[1], bytes([97 + rank]) * world)
+
+            def alloc_fd():
+                log.append("alloc_fd")
+                return pipe[0] if vmm_ok else None
+
+            def attach_fd(fds):
+                log.append("attach_fd")
+                return all(os.read(f, 1) == bytes([97 + r]) for r, f in enumerate(fds) if r != rank)
+
+            def alloc_ipc():
+                log.append("alloc_ipc")
+                return bytes([rank]) * 64
+
+            def attach_ipc(handles):
+                log.append("attach_ipc")
+                assert handles == [bytes([r]) * 64 for r in range(world)]
+
+            return alloc_fd, attach_fd, lambda: log.append("free"), alloc_ipc, attach_ipc
+
+        kind, extras = multigpu.share_windows(*make(True), dist, None, piggyback=("gram", rank))
+        assert kind == "vmm" and extras == [("gram", r) for r in range(world)]
+        assert log == ["alloc_fd", "attach_fd"]
+        del log[:]
+        kind, extras = multigpu.share_windows(*make(rank != 1), dist, None, piggyback=rank * 10)
+        assert kind == "ipc" and extras == [r * 10 for r in range(world)]
+        assert log == (["alloc_fd", "alloc_ipc", "attach_ipc"] if rank == 1 else
+                       ["alloc_fd", "free", "alloc_ipc", "attach_ipc"])
+        del log[:]
+        kind, extras = multigpu.share_windows(*make(True), dist, None, piggyback=None, prefer_vmm=False)
+        assert kind == "ipc" and extras == [None] * world and log == ["alloc_ipc", "attach_ipc"]
         # 2. sharded gradient algebra on an uneven split
         rng = np.random.default_rng(0)
         n, d = 1001, 17
@@ -94,3 +133,19 @@ def test_world2_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == ["ok", "ok"], res
     assert res[0][2] == (0, 500) and res[1][2] == (500, 1001)
+
+
+def test_world3_gloo():
+    """Three ranks: every descriptor / handle reaches every peer (uneven shard sizes too)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == ["ok"] * 3, res
+    assert [r[2] for r in res] == [(0, 333), (333, 667), (667, 1001)]
