@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfos_b200.so")
+# FOS_LIB_PATH: load another build of the library (A/B builds: `python -m fastoptsolver_b200.build --lean`)
+LIB_PATH = os.environ.get("FOS_LIB_PATH") or os.path.join(HERE, "libfos_b200.so")
 
 FOS_OK = 0
 FOS_ERR_INVALID = -1

@@ -44,8 +44,15 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant="name" + defines=("-DX=1", ...): an A/B build written to libfos_b200_<name>.so (own
+    object directory); select it at run time with FOS_LIB_PATH."""
+    global OUT, OBJDIR
     nvcc = _nvcc()
+    extra = list(defines)
+    if variant:
+        OUT = os.path.join(HERE, f"libfos_b200_{variant}.so")
+        OBJDIR = os.path.join(HERE, "csrc", f"_obj_{variant}")
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "fos.h"))
@@ -56,7 +63,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -83,5 +90,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant,
+                 defines=[a for a in sys.argv[1:] if a.startswith("-D")])
     print(path)

@@ -131,10 +131,12 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     }
     double s1 = 0.0, s2 = 0.0;
 
-    // b values of the next two stages, prefetched by lanes < R of warp 0
-    const bool b_lane = use_b && warp == 0 && lane < R;
-    const double* bp = a.b + lo + lane;
-    long long b_left = hi - lo - lane;  // rows remaining for this lane's prefetch stream
+    // b values of the next two stages, prefetched by lanes < R of both half-warps of warp 0 (each
+    // half subtracts b from the dot it ends up holding, see the paired butterfly below)
+    const int blane = lane & 15;
+    const bool b_lane = use_b && warp == 0 && blane < R;
+    const double* bp = a.b + lo + blane;
+    long long b_left = hi - lo - blane;  // rows remaining for this lane's prefetch stream
     double b_cur = 0.0, b_nxt = 0.0;
     if (b_lane && b_left > 0) b_cur = __ldg(bp);
     if (b_lane && b_left > R) b_nxt = __ldg(bp + R);
@@ -197,19 +199,38 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 d2[r] = DOT2 ? p2[0] + p2[1] : 0.0;
             }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (GRAD) d1[r] = fos_warp_sum(d1[r]);
-            if (DOT2) d2[r] = fos_warp_sum(d2[r]);
-        }
         const int par = s & 1;
+        if (GRAD && DOT2) {
+            // one butterfly for both dots (10 instead of 20 SHFL per row): after the first exchange the lower half-warp carries the
+            // pair sums of dot 1 and the upper half those of dot 2; the remaining levels stay inside
+            // a half.  Operands and their order are those of two separate butterflies: same bits.
+            const bool upper = (lane & 16) != 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (lane == r) {
-                // warp 0 folds -b_i into its partial so that the ordered sum below yields r_i
-                const double bi = (warp == 0) ? b_cur : 0.0;
-                *reinterpret_cast<double2*>(&sm.red[par][r][warp][0]) =
-                    make_double2(GRAD ? d1[r] - bi : 0.0, DOT2 ? d2[r] - bi : 0.0);
+            for (int r = 0; r < R; ++r) {
+                const double keep = upper ? d2[r] : d1[r];
+                const double send = upper ? d1[r] : d2[r];
+                double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (blane == r) {
+                    // warp 0 folds -b_i into its partial so that the ordered sum below yields r_i
+                    const double bi = (warp == 0) ? b_cur : 0.0;
+                    sm.red[par][r][warp][upper ? 1 : 0] = v - bi;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (GRAD) d1[r] = fos_warp_sum(d1[r]);
+                if (DOT2) d2[r] = fos_warp_sum(d2[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (lane == r) {
+                    const double bi = (warp == 0) ? b_cur : 0.0;
+                    *reinterpret_cast<double2*>(&sm.red[par][r][warp][0]) =
+                        make_double2(GRAD ? d1[r] - bi : 0.0, DOT2 ? d2[r] - bi : 0.0);
+                }
             }
         }
         __syncthreads();
@@ -225,7 +246,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                      &sm.full_bar[slot], pol);
         }
 
-        // ordered (pairwise tree) sum over the NW warp partials; all loads issue first
+        // ordered (pairwise tree) sum over the NW warp partials; all loads issue first.  The second
+        // dot's total and the squared-residual sums are only ever stored by thread 0, so only warp 0
+        // forms them.
+        const bool sums_here = (warp == 0);
         double r1[R], r2[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -237,7 +261,7 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
 #pragma unroll
                 for (int w = 0; w + span < NW; w += 2 * span) {
                     if (GRAD) pr[w].x += pr[w + span].x;
-                    if (DOT2) pr[w].y += pr[w + span].y;
+                    if (DOT2 && sums_here) pr[w].y += pr[w + span].y;
                 }
             r1[r] = pr[0].x;
             r2[r] = pr[0].y;
@@ -250,11 +274,13 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[j][e] = fma(r1[r], av[r][j][e], acc[j][e]);
         }
+        if (sums_here) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < rows) {
-                if (GRAD) s1 = fma(r1[r], r1[r], s1);
-                if (DOT2) s2 = fma(r2[r], r2[r], s2);
+            for (int r = 0; r < R; ++r) {
+                if (r < rows) {
+                    if (GRAD) s1 = fma(r1[r], r1[r], s1);
+                    if (DOT2) s2 = fma(r2[r], r2[r], s2);
+                }
             }
         }
         b_cur = b_nxt;
