@@ -42,7 +42,9 @@ def test_struct_layout_matches_header():
     from fastoptsolver_b200 import _lib
     # field order of the ctypes mirrors == field order in the header
     header = open(os.path.join(ROOT, "include", "fos.h")).read()
-    for cname, cls in (("fos_pg_params", _lib.PGParams), ("fos_pg_result", _lib.PGResult)):
+    for cname, cls in (("fos_pg_params", _lib.PGParams), ("fos_pg_result", _lib.PGResult),
+                       ("fos_lbfgs_params", _lib.LbfgsParams), ("fos_lbfgs_result", _lib.LbfgsResult),
+                       ("fos_path_params", _lib.PathParams), ("fos_path_result", _lib.PathResult)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -141,3 +143,37 @@ def test_dropin_modules_have_reference_names():
         sys.path.remove(d)
         for m in ("iterative_solvers", "prox_operators", "objective_functions", "lbfgs", "easy_boston_data"):
             sys.modules.pop(m, None)
+
+
+def test_struct_offsets_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays them out from include/fos.h == the ctypes
+    mirrors (a C caller and the Python binding see the same bytes)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from fastoptsolver_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"fos_pg_params": _lib.PGParams, "fos_pg_result": _lib.PGResult,
+               "fos_lbfgs_params": _lib.LbfgsParams, "fos_lbfgs_result": _lib.LbfgsResult,
+               "fos_path_params": _lib.PathParams, "fos_path_result": _lib.PathResult}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fos.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        c, f, v = ln.split()
+        got[(c, f)] = int(v)
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
