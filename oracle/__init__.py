@@ -6,7 +6,10 @@ objective_functions.py, lbfgs.py).  It exists so that the CUDA path can be
 checked on a box where /root/reference is absent.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
 of ``bench.py`` may import it; the product package ``fastoptsolver_b200`` never
-does (tests/test_no_oracle_in_product.py enforces that).
+does (tests/test_library_cpu.py::test_product_never_imports_oracle enforces that).
+``oracle.lbfgs_model`` / ``oracle.gram_model`` restate two pieces of the PRODUCT's own algorithms
+(the device L-BFGS driver, the Gram-matrix formulation) so that their equivalence with the
+reference's formulation can be pinned on the CPU.
 
 Parity status: PINNED.  The reference ships no tests or golden vectors
 (SURVEY.md section 8c), so the pins are outputs of the unmodified reference,
