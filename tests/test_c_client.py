@@ -25,7 +25,9 @@ def client(tmp_path_factory):
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("gcc not available")
-    from fastoptsolver_b200 import _lib
+    from fastoptsolver_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
     _lib.load()
     exe = str(tmp_path_factory.mktemp("c_client") / "c_client")
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
