@@ -265,7 +265,10 @@ def as_design(A, b=None, device=0):
 def _evict(key):
     # dropping the entry drops the cache's reference: the device copy is freed by the
     # DeviceDesign finalizer unless the caller still holds the handle
-    _CACHE.pop(key, None)
+    try:
+        _CACHE.pop(key, None)
+    except Exception:       # interpreter shutdown: module globals may already be gone
+        pass
 
 
 def find_by_matrix(A, device=0):
