@@ -7,7 +7,10 @@ gradient / objective / power iteration; everything under test is product code):
 * ista() on arbitrary Python callables (the reference's loop semantics, iterative_solvers.py:65-125),
   including Armijo counts, step history and the tolerance stop;
 * compute_objective's "residual first, then validate reg_type" order (objective_functions.py:13,28);
-* the metric lists shared between the modules.
+* the metric lists shared between the modules;
+* fista / fista_delta / device-loop ista on top of a numpy model of the ``fos_prox_grad`` contract
+  (oracle/pg_model.py) plugged in where the CUDA library sits: which terms each wrapper records,
+  L + alpha2, history layouts, metrics, exceptions -- every golden trace.
 """
 import numpy as np
 import pytest
@@ -129,3 +132,120 @@ def test_compute_objective_validates_after_the_residual_pass(standin):
         OPS.compute_objective(x, A, b, "l0", 1.0, 1.0)
     assert len(standin) == n_before + 1 and standin[-1].calls["objective"] == 1   # the pass ran first
     assert isinstance(OPS.compute_objective(x, A, b, "lasso", 0.1, 0.0), np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# fista / fista_delta / ista (device-loop flavour) with the engine replaced by its numpy model
+# ------------------------------------------------------------------------------------------------
+class _StandInDesignPG(_StandInDesign):
+    handle = None
+
+    def power_iter(self, v0, n_iter=100, tol=1e-6):
+        v = np.asarray(v0, dtype=np.float64)
+        prev, L, steps = 0.0, 0.0, 0
+        for _ in range(n_iter):
+            w = self.A.T @ (self.A @ v)
+            L = np.linalg.norm(w)
+            v = w / L
+            steps += 1
+            if abs(L - prev) < tol:
+                break
+            prev = L
+        return float(L), steps, 0.0
+
+    def upload_gram(self):
+        return {"ptr": None, "state": 0, "copy_ms": 0.0, "tail_ms": 0.0}
+
+    def comm_info(self):
+        return 0, 1
+
+
+@pytest.fixture
+def engine_model(monkeypatch):
+    """The product's Python layer with (a) a numpy design and (b) a fake library whose fos_prox_grad
+    reads the real PGParams struct, runs oracle/pg_model.py and fills the real PGResult buffers."""
+    import types
+
+    from fastoptsolver_b200 import _lib
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200 import operators as OPS
+    from oracle.pg_model import prox_grad_model
+
+    def as_design(A, b=None, device=0):
+        if isinstance(A, _StandInDesignPG):
+            return A
+        des = _StandInDesignPG(A, b)
+        des.handle = des
+        return des
+
+    def fos_prox_grad(handle, p_ref, r_ref):
+        p, r = p_ref._obj, r_ref._obj
+        des = handle
+        d = des.shape[1]
+        x0 = np.ctypeslib.as_array(p.x0, shape=(d,)).copy() if p.x0 else None
+        out = prox_grad_model(des.A, des.b, scheme=p.scheme, alpha1=p.alpha1, alpha2=p.alpha2, obj_terms=p.obj_terms,
+                              delta=p.delta, backtracking=bool(p.backtracking), eta=p.eta, armijo_c=p.armijo_c,
+                              step0=p.step0, max_iter=p.max_iter, tol=p.tol, tol_ratio=p.tol_ratio,
+                              adaptive_restart=bool(p.adaptive_restart), restart_threshold=p.restart_threshold, x0=x0)
+        it, K = out["n_iters"], p.max_iter
+        np.ctypeslib.as_array(r.x, shape=(d,))[:] = out["x"]
+        if p.want_history and r.x_hist:
+            np.ctypeslib.as_array(r.x_hist, shape=(K + 1, d))[: it + 1] = np.array(out["x_hist"])
+        if it:
+            np.ctypeslib.as_array(r.obj_hist, shape=(max(K, 1),))[:it] = out["obj_hist"]
+            np.ctypeslib.as_array(r.step_hist, shape=(max(K, 1),))[:it] = out["step_hist"]
+            np.ctypeslib.as_array(r.ls_iters, shape=(max(K, 1),))[:it] = out["ls_iters"]
+            np.ctypeslib.as_array(r.ls_ms, shape=(max(K, 1),))[:it] = 1e-3
+        np.ctypeslib.as_array(r.t_hist, shape=(K + 1,))[: it + 1] = out["t_hist"]
+        np.ctypeslib.as_array(r.grad_ms, shape=(K + 1,))[: out["n_grad_calls"]] = 1e-3
+        r.n_iters, r.n_grad_calls, r.n_passes, r.stop_reason = it, out["n_grad_calls"], out["n_grad_calls"], out["stop_reason"]
+        return 0
+
+    fake = types.SimpleNamespace(fos_prox_grad=fos_prox_grad)
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    monkeypatch.setattr(S, "as_design", as_design)
+    monkeypatch.setattr(S, "find_by_matrix", lambda A, device=0: A if isinstance(A, _StandInDesignPG) else None)
+    monkeypatch.setattr(OPS, "as_design", as_design)
+    return harness.Backend(name="product-on-engine-model", fista=S.fista, fista_delta=S.fista_delta, ista=S.ista,
+                           estimate_lipschitz=S.estimate_lipschitz, lbfgs_cls=None, ista_callables=OPS.ista_callables,
+                           ls_iters=lambda: list(S.ls_call_iters), grad_calls=lambda: len(S.grad_call_times))
+
+
+@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("fista", "fista_delta", "ista")))
+def test_python_layer_on_engine_model_against_golden(engine_model, name, key):
+    out, spec = harness.run_case(engine_model, name, key)
+    harness.check_case(out, spec, name, key, 1e-10)
+
+
+def test_python_layer_quirks_on_engine_model(engine_model):
+    be = engine_model
+    A, b = cases.design("c1")
+    np.random.seed(0)
+    x1 = be.fista(A, b, "bogus", 1.0, 0.0, max_iter=5)           # reg_type accepted and ignored
+    np.random.seed(0)
+    x2 = be.fista(A, b, "lasso", 1.0, 0.0, max_iter=5)
+    np.testing.assert_array_equal(x1, x2)
+    with pytest.raises(AssertionError):
+        be.fista_delta(A, b, "lasso", 1.0, 0.0, 2.0)
+    np.random.seed(0)
+    be.fista_delta(A, b, "bogus", 1.0, 0.0, 3.0, max_iter=3)     # unknown reg_type only matters with history
+    with pytest.raises(ValueError, match="Unsupported reg_type='bogus'"):
+        be.fista_delta(A, b, "bogus", 1.0, 0.0, 3.0, max_iter=3, return_history=True)
+    np.random.seed(0)
+    _, h = be.fista(A, b, "lasso", 1.0, 0.0, max_iter=7, return_history=True)
+    assert (len(h["x"]), len(h["obj"])) == (8, 7)
+    h["x"][0][0] = 123.0
+    assert h["x"][1][0] != 123.0                                  # independent copies
+    np.random.seed(0)
+    _, h = be.fista_delta(A, b, "lasso", 1.0, 0.0, 3.0, max_iter=7, return_history=True)
+    assert (len(h["x"]), len(h["obj"])) == (7, 7)
+    np.random.seed(0)
+    x0, h0 = be.fista(A, b, "lasso", 1.0, 0.0, max_iter=0, return_history=True)
+    assert np.all(x0 == 0) and len(h0["x"]) == 1 and h0["obj"] == []
+    # the reference draws randn(d) once per solver call: the global stream advances identically
+    np.random.seed(5)
+    be.fista(A, b, "lasso", 1.0, 0.0, max_iter=2)
+    after = np.random.rand()
+    np.random.seed(5)
+    oracle.fista(A, b, "lasso", 1.0, 0.0, max_iter=2)
+    assert after == np.random.rand()
