@@ -4,11 +4,12 @@ A^T(Ay - b) = sum_g A_g^T (A_g y - b_g) over contiguous row blocks, so the only 
 step of the hot path is one all-reduce of the (d + 2)-vector [A_g^T r_g, ||r_g||^2,
 ||A_g x - b_g||^2] per pass.  That all-reduce is fused into the epilogue kernel over
 peer memory (csrc/epilogue_kernels.cu: peer_exchange): every rank publishes its partial in
-an IPC-mapped window, signals its peers over NVLink and sums all windows in rank order, so
+a window mapped into every peer, signals its peers over NVLink and sums all windows in rank order, so
 all ranks hold bit-identical iterates and the solver state is simply replicated.
 
-torch.distributed is plumbing here: it carries the 64-byte IPC handles once and provides
-the barriers around timed regions; the data path never calls NCCL.
+torch.distributed is plumbing here: it wires the windows once (socket names / handles and an
+agreement flag ride on two object all-gathers) and provides the barriers around timed regions;
+the data path never calls NCCL.
 """
 from __future__ import annotations
 
