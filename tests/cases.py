@@ -24,6 +24,10 @@ DESIGNS = {
     "mid32": dict(store=False),  # same, A stored as float32
     "odd": dict(store=False),    # 500 x 37  (odd d: padded leading dimension on device)
     "wide": dict(store=False),   # 1500 x 640 (streaming kernel, d >= 512)
+    # 2000 x 64, option combinations off the figure-legend grid (restart thresholds, ratio stops with
+    # backtracking, steep / shallow Armijo factors, non-zero ISTA start, capped L-BFGS).  Pins the
+    # oracle and the host layer on the CPU; staged for the GPU suite (cpu_only) until it has run there.
+    "midx": dict(store=False, cpu_only=True),
 }
 
 
@@ -66,6 +70,8 @@ def design(name):
         return _elementwise_design(500, 37, 12, 1.0)
     if name == "wide":
         return _elementwise_design(1500, 640, 13, 2.0)
+    if name == "midx":
+        return _elementwise_design(2000, 64, 21, 0.8)
     raise KeyError(name)
 
 
@@ -82,6 +88,8 @@ def solver_specs(name, A, b):
     them back so both sides see identical scalars."""
     lam = float(np.max(np.abs(np.asarray(A, dtype=np.float64).T @ b)))
     a1 = 0.1 * lam
+    if name == "midx":
+        return _extra_specs(lam)
     regs = {"lasso": (a1, 0.0), "elasticnet": (a1, 0.5 * a1)}
     specs = {}
     full_grid = name in ("c1", "mid")
@@ -125,6 +133,55 @@ def solver_specs(name, A, b):
     for s in specs.values():
         s.setdefault("np_seed", 0)
     return specs
+
+
+def _extra_specs(lam):
+    """Option combinations beyond the figure-legend grid (design "midx")."""
+    a1, a2 = 0.08 * lam, 0.03 * lam
+    S = {}
+
+    def add(key, solver, reg, x1, x2, kw, **extra):
+        S[key] = dict(solver=solver, reg_type=reg, alpha1=x1, alpha2=x2, kw=kw, **extra)
+
+    add("fista/restart-thr0.5", "fista", "lasso", 0.02 * lam, 0.0,
+        dict(max_iter=150, adaptive_restart=True, restart_threshold=0.5))
+    add("fista/restart-armijo", "fista", "elasticnet", 0.02 * lam, a2,
+        dict(max_iter=80, adaptive_restart=True, restart_threshold=1.2, backtracking=True, t_init_factor=3.0))
+    add("fista/tolratio-armijo", "fista", "lasso", a1, 0.0,
+        dict(max_iter=200, tol_ratio=0.25, backtracking=True, t_init_factor=2.0))
+    add("fista/steep-armijo", "fista", "elasticnet", a1, a2,
+        dict(max_iter=40, backtracking=True, t_init_factor=8.0, eta=0.3))
+    add("fista/shallow-armijo", "fista", "lasso", a1, 0.0,
+        dict(max_iter=40, backtracking=True, t_init_factor=5.0, eta=0.9))
+    add("fista/half-step", "fista", "lasso", a1, 0.0, dict(max_iter=60, t_init_factor=0.5))
+    add("fista/one-iteration", "fista", "elasticnet", a1, a2, dict(max_iter=1))
+    add("fista/gradnorm-stop", "fista", "ridge", 0.0, a2, dict(max_iter=400, tol=1e-2))
+    add("fista_delta/tolratio", "fista_delta", "lasso", a1, 0.0, dict(max_iter=300, tol_ratio=0.6), delta=3.5)
+    add("fista_delta/delta10-armijo", "fista_delta", "elasticnet", a1, a2,
+        dict(max_iter=60, backtracking=True, t_init_factor=2.0, eta=0.8), delta=10.0)
+    # reg_type picks the recorded objective only: "ridge" with alpha1 > 0 still thresholds the iterates
+    add("fista_delta/ridge-objective-with-l1-prox", "fista_delta", "ridge", a1, a2, dict(max_iter=40), delta=3.0)
+    add("fista_delta/step-stop", "fista_delta", "elasticnet", a1, a2, dict(max_iter=500, tol=1e-5), delta=2.5)
+    add("ista/steep-armijo", "ista", "elasticnet", a1, a2,
+        dict(max_iter=60, backtracking=True, t_init_factor=6.0, eta=0.3))
+    add("ista/tol-armijo", "ista", "lasso", a1, 0.0, dict(max_iter=400, tol=1e-4, backtracking=True, t_init_factor=2.0))
+    add("ista/nonzero-start", "ista", "lasso", a1, 0.0, dict(max_iter=50), x0_seed=17)
+    add("ista/nonzero-start-armijo", "ista", "elasticnet", a1, a2,
+        dict(max_iter=50, backtracking=True, t_init_factor=2.0), x0_seed=18)
+    add("lbfgs/capped", "lbfgs", "ridge", a1, a2, dict(max_iter=3))
+    add("lbfgs/loose-tol", "lbfgs", "elasticnet", a1, a2, dict(max_iter=200, tol=1e-1))
+    add("lbfgs/tiny-alpha1", "lbfgs", "elasticnet", 1e-9, a2, dict(max_iter=100))
+    add("lbfgs/tiny-alpha2", "lbfgs", "elasticnet", a1, 1e-9, dict(max_iter=100))
+    for s in S.values():
+        s.setdefault("np_seed", 3)
+    return S
+
+
+def ista_start(spec, d):
+    """Start point of an ISTA case: zeros unless the spec names a seed."""
+    if "x0_seed" in spec:
+        return np.random.default_rng(spec["x0_seed"]).standard_normal(d) * 0.3
+    return np.zeros(d)
 
 
 def prox_probe_vector():

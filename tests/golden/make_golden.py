@@ -63,7 +63,7 @@ def run_solver_case(A, b, spec):
         if a2 > 0:
             L += a2
         g, grad_g, prox_h = cases.ista_callables_numpy(A, b, a1, a2, ref_prox.prox_l1)
-        x, h = ref_is.ista(np.zeros(d), g, grad_g, prox_h, L, return_history=True, **spec["kw"])
+        x, h = ref_is.ista(cases.ista_start(spec, d), g, grad_g, prox_h, L, return_history=True, **spec["kw"])
         out.update(x=x, hx=_stack(h["x"], d), ht=np.array(h["t"]), hdelta=np.array(h["delta"]),
                    L=np.float64(L))
     elif kind == "lbfgs":
@@ -82,8 +82,27 @@ def run_solver_case(A, b, spec):
     return out
 
 
+def traces(names):
+    for name in names:
+        A, b = cases.design(name)
+        blob = {}
+        if cases.DESIGNS[name].get("store"):
+            blob["A"] = A
+            blob["b"] = b
+        for key, spec in cases.solver_specs(name, A, b).items():
+            res = run_solver_case(A, b, spec)
+            for k, val in res.items():
+                blob[f"{key}/{k}"] = val
+            print(f"{name:10s} {key:40s} iters={len(res.get('hobj', res.get('hdelta', [])))} "
+                  f"grad_calls={int(res['grad_num_calls'])} ls_total={int(res['ls_iters'].sum())}")
+        np.savez_compressed(os.path.join(HERE, f"traces_{name}.npz"), **blob)
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
+    if len(sys.argv) > 1:
+        # only the named designs' traces (leaves the other fixtures byte-identical)
+        return traces(sys.argv[1:])
 
     # ---- data generator: reference arrays for the d == 5 check
     A, b, xt = ref_data.generate_correlated_boston_like_data()
@@ -116,19 +135,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "operators.npz"), **ops)
 
     # ---- solver traces
-    for name in cases.DESIGNS:
-        A, b = cases.design(name)
-        blob = {}
-        if cases.DESIGNS[name].get("store"):
-            blob["A"] = A
-            blob["b"] = b
-        for key, spec in cases.solver_specs(name, A, b).items():
-            res = run_solver_case(A, b, spec)
-            for k, val in res.items():
-                blob[f"{key}/{k}"] = val
-            print(f"{name:10s} {key:40s} iters={len(res.get('hobj', res.get('hdelta', [])))} "
-                  f"grad_calls={int(res['grad_num_calls'])} ls_total={int(res['ls_iters'].sum())}")
-        np.savez_compressed(os.path.join(HERE, f"traces_{name}.npz"), **blob)
+    traces(list(cases.DESIGNS))
 
 
 if __name__ == "__main__":

@@ -68,10 +68,14 @@ def golden_keys(name):
     return sorted({k.rsplit("/", 1)[0] for k in g if "/" in k})
 
 
-def all_case_ids(solvers=None, designs=None):
+def all_case_ids(solvers=None, designs=None, include_cpu_only=False):
+    """(design, key) pairs of the golden traces.  Designs flagged ``cpu_only`` (staged: pinned on the
+    CPU, not yet run on a GPU) are left out unless asked for."""
     out = []
     for name in cases.DESIGNS:
         if designs and name not in designs:
+            continue
+        if cases.DESIGNS[name].get("cpu_only") and not include_cpu_only:
             continue
         for key in golden_keys(name):
             if solvers and key.split("/")[0] not in solvers:
@@ -101,7 +105,7 @@ def run_case(backend: Backend, name: str, key: str):
         if a2 > 0:
             L += a2
         gfun, grad_g, prox_h = backend.ista_callables(A, b, a1, a2)
-        x, h = backend.ista(np.zeros(d), gfun, grad_g, prox_h, L, return_history=True, **spec["kw"])
+        x, h = backend.ista(cases.ista_start(spec, d), gfun, grad_g, prox_h, L, return_history=True, **spec["kw"])
         out.update(x=x, hx=h["x"], ht=h["t"], hdelta=h["delta"], L=L)
     elif kind == "lbfgs":
         s = backend.lbfgs_cls(spec["reg_type"], a1, a2, **spec["kw"])

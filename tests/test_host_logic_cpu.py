@@ -64,7 +64,7 @@ def standin(monkeypatch):
     return made
 
 
-@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("lbfgs",)))
+@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("lbfgs",), include_cpu_only=True))
 def test_lbfgs_wrapper_against_golden(standin, name, key):
     from fastoptsolver_b200 import iterative_solvers as S
     from fastoptsolver_b200 import lbfgs as LB
@@ -106,7 +106,7 @@ def test_lbfgs_wrapper_quirks(standin):
         LB.LBFGSSolver("ridge", 0.0, 1.0, driver="fortran").fit(A, b)
 
 
-@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("ista",)))
+@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("ista",), include_cpu_only=True))
 def test_ista_on_python_callables_against_golden(name, key):
     """ista() handed plain Python closures runs the reference's loop on the host."""
     from fastoptsolver_b200 import iterative_solvers as S
@@ -211,7 +211,7 @@ def engine_model(monkeypatch):
                            ls_iters=lambda: list(S.ls_call_iters), grad_calls=lambda: len(S.grad_call_times))
 
 
-@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("fista", "fista_delta", "ista")))
+@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("fista", "fista_delta", "ista"), include_cpu_only=True))
 def test_python_layer_on_engine_model_against_golden(engine_model, name, key):
     out, spec = harness.run_case(engine_model, name, key)
     harness.check_case(out, spec, name, key, 1e-10)
