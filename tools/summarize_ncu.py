@@ -76,4 +76,6 @@ def launch_list(path, out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) != 4 or sys.argv[1] not in ("full", "list"):
+        sys.exit(__doc__)
     {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
