@@ -212,11 +212,16 @@ int fos_balance_rows(fos_design* h) {
     const int P = h->n_parts;
     if (h->kern_kind != 1 || P != h->sm_count || P > 256) return FOS_OK;
     if (h->n < 256LL * P) return FOS_OK;  // too few stages per CTA for the weights to matter
-    // slot table: identity (SM ids are 0..sm_count-1)
-    std::vector<int> slot(256, 0);
-    for (int i = 0; i < 256; ++i) slot[i] = (i < P) ? i : (i % P);
-    if (h->sm_slot == nullptr) FOS_CUDA(cudaMalloc(&h->sm_slot, 256 * sizeof(int)));
-    FOS_CUDA(cudaMemcpy(h->sm_slot, slot.data(), 256 * sizeof(int), cudaMemcpyHostToDevice));
+    // slot table: SM id -> preferred slot (identity when the SM ids are 0..sm_count-1), followed by
+    // one claim word per slot.  The table is a preference only: the kernel claims its slot with an
+    // atomic exchange of the launch's pass number and walks on if it is taken, so a pass covers
+    // every row block exactly once whatever the placement of the CTAs (%smid is not guaranteed to
+    // be contiguous, and other work may hold some SMs).
+    std::vector<int> slot(256 + P, 0);
+    for (int i = 0; i < 256; ++i) slot[i] = i % P;
+    for (int i = 0; i < P; ++i) slot[256 + i] = -1;  // 0xFFFFFFFF: never a pass number (31 bits)
+    if (h->sm_slot == nullptr) FOS_CUDA(cudaMalloc(&h->sm_slot, slot.size() * sizeof(int)));
+    FOS_CUDA(cudaMemcpy(h->sm_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice));
 
     std::lock_guard<std::mutex> lock(g_bal_mutex);
     const auto key = std::make_pair(h->device, P);
@@ -229,10 +234,12 @@ int fos_balance_rows(fos_design* h) {
         std::vector<double> w(P, 1.0), best_w(P, 1.0), dur(P);
         double best_T = 1e300;
         int status = FOS_OK;
+        bool usable = true;
         for (int round = 0; round < 6 && status == FOS_OK; ++round) {
             apply_weights(h, w);
             cudaMemcpy(h->row_lo, h->row_lo_host.data(), (P + 1) * sizeof(long long), cudaMemcpyHostToDevice);
             status = fos_launch_grad(h, GM_GRAD | GM_DOT2);
+            cudaMemsetAsync(buf, 0, t.size() * sizeof(unsigned long long), h->stream);
             h->cta_times = buf;
             if (status == FOS_OK) status = fos_launch_grad(h, GM_GRAD | GM_DOT2);
             h->cta_times = nullptr;
@@ -245,6 +252,14 @@ int fos_balance_rows(fos_design* h) {
                 status = FOS_ERR_CUDA;
                 break;
             }
+            // every slot must have been run exactly once, by a CTA sitting on the SM the table maps
+            // to it; otherwise the SM-indexed weights mean nothing on this device / in this process
+            // state and the design keeps its equal, blockIdx-indexed blocks
+            for (int c = 0; c < P && usable; ++c) {
+                const unsigned long long smid = t[2 * c + 1] >> 48;
+                if (t[2 * c] == 0 || t[2 * c + 1] == 0 || static_cast<int>(smid % P) != c) usable = false;
+            }
+            if (!usable) break;
             unsigned long long t0 = ~0ull, t1 = 0;
             double mean = 0.0;
             for (int c = 0; c < P; ++c) {
@@ -273,7 +288,16 @@ int fos_balance_rows(fos_design* h) {
         cudaMemsetAsync(h->partial_s, 0, static_cast<size_t>(P) * 2 * sizeof(double), h->stream);
         cudaStreamSynchronize(h->stream);
         if (status != FOS_OK) return status;
+        if (!usable) best_w.clear();  // remembered: this device does not get SM-indexed blocks
         it = g_bal_weights.emplace(key, best_w).first;
+    }
+    if (it->second.empty()) {
+        // equal blocks indexed by blockIdx (the default partition)
+        cudaFree(h->sm_slot);
+        h->sm_slot = nullptr;
+        for (int c = 0; c <= P; ++c) h->row_lo_host[c] = (h->n * c) / P;
+        FOS_CUDA(cudaMemcpy(h->row_lo, h->row_lo_host.data(), (P + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+        return FOS_OK;
     }
     apply_weights(h, it->second);
     FOS_CUDA(cudaMemcpy(h->row_lo, h->row_lo_host.data(), (P + 1) * sizeof(long long), cudaMemcpyHostToDevice));

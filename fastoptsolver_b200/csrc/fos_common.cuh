@@ -126,7 +126,9 @@ struct GradArgs {
     int d, lda, ldv;
     int mode_override;   // >= 0: use instead of ctrl->g_mode
     const long long* row_lo;        // [n_parts + 1] row partition of the streaming kernel
-    const int* sm_slot;             // [256] SM id -> partition slot (nullable: slot = blockIdx.x)
+    const int* sm_slot;             // [256] SM id -> preferred partition slot (nullable: slot = blockIdx.x)
+    unsigned* slot_claim;           // [n_parts] pass number that last claimed each slot (with sm_slot)
+    unsigned pass_no;               // number of this launch (monotonic per design): the claim token
     unsigned long long* cta_times;  // debug: [n_parts][2] start/end %globaltimer per CTA (nullable)
 };
 
@@ -195,7 +197,8 @@ struct fos_design {
     unsigned long long* cta_times = nullptr;  // debug buffer (fos_debug_cta_times)
     long long* row_lo = nullptr;              // device: [n_parts + 1] row partition (streaming kernel)
     std::vector<long long> row_lo_host;
-    int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed
+    int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed;
+                                              // followed by n_parts claim words (GradArgs::slot_claim)
     bool balanced = false;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
     void* arena = nullptr;         // grow-only device workspace of the per-solve arrays (fos_arena_reserve)

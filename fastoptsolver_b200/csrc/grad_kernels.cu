@@ -324,34 +324,39 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     __shared__ __align__(16) StreamSmem<NW, R> sm;
 
     const int tid = threadIdx.x;
-    const int ncta = gridDim.x;
+    __shared__ int s_cta;
     // Partition slot of this CTA.  With one persistent CTA per SM the slot can be tied to the SM
     // the CTA landed on (the block scheduler's blockIdx -> SM map changes from launch to launch),
-    // which lets the row blocks be weighted by the SMs' measured streaming rates.
-    int cta = blockIdx.x;
-    if (a.sm_slot != nullptr) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        cta = a.sm_slot[smid & 255u];
-    }
-
-    // static contiguous row partition (table built once per design): deterministic summation
-    // order, bit-reproducible results for the lifetime of the design.
-    const long long lo = a.row_lo[cta];
-    const long long hi = a.row_lo[cta + 1];
-    const int nst = static_cast<int>((hi - lo + R - 1) / R);
-    (void)ncta;
-
+    // which lets the row blocks be weighted by the SMs' measured streaming rates.  %smid is only a
+    // preference: the slot is CLAIMED with an atomic exchange of this launch's pass number, and a
+    // CTA whose preferred slot is already taken (two CTAs on one SM because other work holds some
+    // SMs, non-contiguous SM ids) walks on to the next free one -- P CTAs, P slots, so every row
+    // block is processed exactly once per pass whatever the placement.
     uint64_t pol = 0;
     if (tid == 0) {
+        int cta0 = blockIdx.x;
+        if (a.sm_slot != nullptr) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int P = gridDim.x;
+            int s = a.sm_slot[smid & 255u];
+            for (int k = 0; k < P; ++k, s = (s + 1 == P) ? 0 : s + 1)
+                if (atomicExch(&a.slot_claim[s], a.pass_no) != a.pass_no) break;
+            cta0 = s;
+        }
+        s_cta = cta0;
+        // static contiguous row partition (table built once per design): deterministic summation
+        // order, bit-reproducible results for the lifetime of the design.
+        const long long lo0 = a.row_lo[cta0], hi0 = a.row_lo[cta0 + 1];
+        const int nst0 = static_cast<int>((hi0 - lo0 + R - 1) / R);
         for (int s = 0; s < nstage; ++s) mbar_init(&sm.full_bar[s], 1);
         mbar_fence_init();
         // prologue: fill the ring (thread 0 is also the only thread that refills it later)
         pol = l2_evict_first_policy();
         const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
-        for (int s = 0; s < nstage && s < nst; ++s) {
-            const long long rs = lo + static_cast<long long>(s) * R;
-            const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
+        for (int s = 0; s < nstage && s < nst0; ++s) {
+            const long long rs = lo0 + static_cast<long long>(s) * R;
+            const int nr = static_cast<int>(min(static_cast<long long>(R), hi0 - rs));
             const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
             mbar_expect_tx(&sm.full_bar[s], bytes);
             bulk_g2s(ring + static_cast<size_t>(s) * stage_bytes,
@@ -360,6 +365,10 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         }
     }
     __syncthreads();
+    const int cta = s_cta;
+    const long long lo = a.row_lo[cta];
+    const long long hi = a.row_lo[cta + 1];
+    const int nst = static_cast<int>((hi - lo + R - 1) / R);
 
     // The ring fill above only touches A, which no kernel ever writes: under programmatic
     // dependent launch it overlaps the tail of the previous epilogue.  Everything below reads
@@ -652,6 +661,8 @@ int fos_launch_grad(fos_design* h, int mode_override) {
     a.cta_times = h->cta_times;
     a.row_lo = h->row_lo;
     a.sm_slot = (h->kern_kind == 1) ? h->sm_slot : nullptr;
+    a.slot_claim = a.sm_slot ? reinterpret_cast<unsigned*>(h->sm_slot + 256) : nullptr;
+    a.pass_no = static_cast<unsigned>(h->launches & 0x7fffffff);
     void* params[3];
     params[0] = &a;
     if (h->kern_kind == 1) {

@@ -1,11 +1,12 @@
-"""DeviceDesign: the pair (A, b) resident in HBM, plus the cache that lets the drop-in
-solvers accept plain numpy arrays the way the reference does.
+"""DeviceDesign: the pair (A, b) resident in HBM, plus the (opt-in) cache that lets the drop-in
+solvers reuse the device copy of plain numpy arrays.
 
-The reference re-reads its numpy arrays on every call (iterative_solvers.py:133-134);
-the notebook calls ~19 solver variants per scenario on the same ``A`` (SURVEY.md section
-7, "A residency").  ``as_design(A, b)`` therefore uploads once and reuses the device copy
-while the host buffers are unchanged (same address, shape, strides, dtype and a strided
-content fingerprint); pass a ``DeviceDesign`` in place of ``A`` to skip even that check.
+The reference re-reads its numpy arrays on every call (iterative_solvers.py:133-134), so by
+default ``as_design(A, b)`` uploads bare host arrays on every call.  The notebook calls ~19
+solver variants per scenario on the same ``A`` ("A residency"): pass a
+``DeviceDesign`` in place of ``A`` to keep it resident, or opt into the cache (``FOS_CACHE=1`` /
+``set_cache(True)``), which reuses a copy only for the same live array object with a matching
+content fingerprint and a matching fresh row sample.
 """
 from __future__ import annotations
 
@@ -38,7 +39,10 @@ class DeviceDesign:
         self.dtype = np.dtype(np.float64 if dtype == _lib.FOS_F64 else np.float32)
         self.device = device
         self._keepalive = keepalive
-        self._finalizer = weakref.finalize(self, _destroy, handle)
+        # shared with the finalizer: was the design closed explicitly, does it hold an exchange
+        # window that peer ranks read (multigpu.attach sets "sharded")
+        self._life = {"explicit": False, "sharded": False}
+        self._finalizer = weakref.finalize(self, _destroy, handle, self._life)
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -97,6 +101,7 @@ class DeviceDesign:
 
     def close(self):
         if self._h is not None:
+            self._life["explicit"] = True
             self._finalizer()
             self._h = None
 
@@ -197,7 +202,14 @@ class DeviceDesign:
         return L.value, its.value, ms.value
 
 
-def _destroy(handle):
+def _destroy(handle, life=None):
+    if life is not None and life.get("sharded") and not life.get("explicit"):
+        # The exchange window of a row-sharded design is read by the peers' epilogue kernels: it must
+        # only go away after a barrier (multigpu.close).  Garbage collection cannot provide one.
+        import warnings
+        warnings.warn("a row-sharded DeviceDesign was reclaimed by the garbage collector; its exchange window "
+                      "is freed without a barrier and a peer still inside a solve may read freed memory -- "
+                      "call fastoptsolver_b200.multigpu.close(design, dist) instead", ResourceWarning, stacklevel=2)
     try:
         _lib.load().fos_design_destroy(C.c_void_p(handle))
     except Exception:
@@ -205,17 +217,48 @@ def _destroy(handle):
 
 
 # ---------------------------------------------------------------------------------- cache
-_CACHE = {}          # key -> (DeviceDesign, fingerprint)
+# The reference re-reads its numpy arrays on every call (iterative_solvers.py:133-134, :173), so a
+# caller may edit ``A`` in place between two solver calls.  A device copy can only be reused on the
+# caller's word that this does not happen: reuse is therefore OPT-IN (``FOS_CACHE=1`` or
+# ``set_cache(True)``); by default every call on bare numpy arrays uploads them again, exactly what
+# the reference's re-read means.  Callers that want residency without the promise pass a
+# ``DeviceDesign`` in place of ``A`` (the sweep driver, the benchmarks).
+_CACHE = {}          # key -> (DeviceDesign, fingerprint, weakref to the host matrix)
 _CACHE_MAX = 4
+_CACHE_ON = None     # None: follow the environment (FOS_CACHE=1); True / False: set_cache()
+_FRESH_ROWS = 16     # rows compared with the device copy, freshly drawn, on every cache hit
+
+
+def set_cache(enabled):
+    """Switch reuse of uploaded host arrays on or off for this process (None: follow FOS_CACHE)."""
+    global _CACHE_ON
+    _CACHE_ON = enabled
+    if not cache_enabled():
+        clear_cache()
+
+
+def cache_enabled():
+    if os.environ.get("FOS_NO_CACHE") == "1":
+        return False
+    if _CACHE_ON is not None:
+        return bool(_CACHE_ON)
+    return os.environ.get("FOS_CACHE") == "1"
 
 
 def _fingerprint_matrix(A):
-    """Content check of A for cache reuse: CRC of ~64k strided samples and of its first and last
-    rows.  (A full CRC of a 32 GB matrix would cost more than re-uploading it.)"""
-    flat_n = A.shape[0] * A.shape[1]
-    step = max(1, flat_n // 65536)
-    idx = np.arange(0, flat_n, step)
-    crc = zlib.crc32(np.ascontiguousarray(A[idx // A.shape[1], idx % A.shape[1]]).tobytes())
+    """Content check of A for cache reuse (a full hash of a 32 GB matrix costs more than uploading it
+    again): CRC of 65536 elements at pseudo-random positions (fixed seed, so two calls sample the same
+    positions whatever the shape -- a fixed stride aliases with the row length), of 64 complete
+    pseudo-random rows (every column is covered: ``A[:, j] = 0`` or a rescaled feature is seen), and of
+    the first and last rows.  Small matrices (<= 1 MB) are hashed completely."""
+    n, d = A.shape
+    if A.size * A.itemsize <= (1 << 20):
+        return zlib.crc32(np.ascontiguousarray(A).tobytes())
+    rng = np.random.default_rng(0x5EED)
+    m = 65536
+    crc = zlib.crc32(np.ascontiguousarray(A[rng.integers(0, n, m), rng.integers(0, d, m)]).tobytes())
+    rows = np.unique(rng.integers(0, n, 64))
+    crc = zlib.crc32(np.ascontiguousarray(A[rows]).tobytes(), crc)
     crc = zlib.crc32(np.ascontiguousarray(A[0]).tobytes(), crc)
     crc = zlib.crc32(np.ascontiguousarray(A[-1]).tobytes(), crc)
     return crc
@@ -226,29 +269,45 @@ def _fingerprint(A, b):
     return _fingerprint_matrix(A), zlib.crc32(np.ascontiguousarray(b).tobytes())
 
 
+def _device_rows_match(des, A):
+    """Freshly drawn rows of the host matrix against the same rows of the device copy, bit for bit.
+    The positions change from call to call (OS entropy; numpy's legacy global stream, which
+    estimate_lipschitz consumes like the reference, is not touched), so an edit the fixed sample
+    missed cannot survive repeated calls."""
+    n = A.shape[0]
+    if not hasattr(des, "download"):
+        return True
+    for r in np.random.default_rng().integers(0, n, min(n, _FRESH_ROWS)):
+        dev, _ = des.download(int(r), 1)
+        if dev.tobytes() != np.ascontiguousarray(A[int(r)], dtype=dev.dtype).tobytes():
+            return False
+    return True
+
+
 def _matrix_key(A):
     return (A.__array_interface__["data"][0], A.shape, A.strides, A.dtype.str)
 
 
 def as_design(A, b=None, device=0):
-    """Return a DeviceDesign for (A, b), uploading only when needed.
+    """Return a DeviceDesign for (A, b).
 
-    A cached device copy is reused only for the *same array objects* (identity, still alive) with
-    unchanged shape/strides/dtype and matching content fingerprint.  The reference re-reads its
-    arrays on every call; if you mutate ``A`` in place between calls in a way the sampled
-    fingerprint cannot see, call ``clear_cache()`` (or set FOS_NO_CACHE=1 to upload every time)."""
+    Default: bare host arrays are uploaded on every call (the reference re-reads them on every
+    call).  With the cache switched on (``FOS_CACHE=1`` / ``set_cache(True)``) a device copy is reused
+    for the *same array objects* (identity, still alive) with unchanged shape/strides/dtype, a
+    matching content fingerprint and a matching fresh row sample; ``FOS_NO_CACHE=1`` overrides."""
     if isinstance(A, DeviceDesign):
         return A
     A = np.asarray(A)
     if b is None:
         raise ValueError("b is required when A is a host array")
     b = np.asarray(b)
-    if os.environ.get("FOS_NO_CACHE") == "1":
+    if not cache_enabled():
         return DeviceDesign.from_host(A, b, device=device)
     key = _matrix_key(A) + (b.__array_interface__["data"][0], b.shape, device)
     fp = _fingerprint(A, b.reshape(-1))
     hit = _CACHE.get(key)
-    if hit is not None and hit[1] == fp and hit[0]._h is not None and hit[2]() is A:
+    if (hit is not None and hit[1] == fp and hit[0]._h is not None and hit[2]() is A
+            and _device_rows_match(hit[0], A)):
         return hit[0]
     des = DeviceDesign.from_host(A, b, device=device)
     if len(_CACHE) >= _CACHE_MAX:
@@ -277,6 +336,8 @@ def find_by_matrix(A, device=0):
     reads b, reuse the copy a solver uploaded."""
     if isinstance(A, DeviceDesign):
         return A
+    if not cache_enabled():
+        return None
     A = np.asarray(A)
     akey = _matrix_key(A)
     fp_a = None
@@ -284,7 +345,7 @@ def find_by_matrix(A, device=0):
         if key[:4] == akey and key[6] == device and des._h is not None and ref() is A:
             if fp_a is None:
                 fp_a = _fingerprint_matrix(A)
-            if fp[0] == fp_a:
+            if fp[0] == fp_a and _device_rows_match(des, A):
                 return des
     return None
 

@@ -48,9 +48,20 @@ def _all_ok(ok: bool, dist, group):
     return all(_gather(bool(ok), dist, group))
 
 
+def _peer_credentials(conn):
+    """(pid, uid, gid) of the process at the other end of a unix socket (SO_PEERCRED)."""
+    import socket
+    import struct
+    raw = conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+    return struct.unpack("3i", raw)
+
+
 class _FdServer:
-    """Hands this rank's descriptor to every peer that connects (unix socket in the abstract
-    namespace, SCM_RIGHTS)."""
+    """Hands this rank's descriptor to every peer rank that connects (unix socket in the abstract
+    namespace, SCM_RIGHTS).  Abstract names are visible to every local process, so a connection
+    only gets the descriptor if the kernel says (SO_PEERCRED) that it comes from this user AND from
+    one of the process ids the ranks published over the process group; anything else is dropped
+    and does not use up one of the world-1 hand-overs."""
 
     def __init__(self, world, timeout=60.0):
         import os
@@ -61,20 +72,29 @@ class _FdServer:
         self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
         self.sock.settimeout(timeout)
         self.sock.bind(self.name)
-        self.sock.listen(world)
+        self.sock.listen(world + 8)
         self.errors = []
+        self.rejected = []
         self.thread = None
 
-    def serve(self, fd):
+    def serve(self, fd, allowed_pids=None):
+        import os
         import socket
         import threading
+        allowed = None if allowed_pids is None else set(int(p) for p in allowed_pids)
 
         def run():
             try:
-                for _ in range(self.world - 1):
+                served = 0
+                while served < self.world - 1:
                     conn, _addr = self.sock.accept()
                     with conn:
+                        pid, uid, _gid = _peer_credentials(conn)
+                        if uid != os.getuid() or (allowed is not None and pid not in allowed):
+                            self.rejected.append((pid, uid))
+                            continue
                         socket.send_fds(conn, [b"w"], [fd])
+                        served += 1
             except Exception as e:      # the receiving side reports the missing descriptor
                 self.errors.append(e)
 
@@ -107,10 +127,12 @@ def exchange_fds(my_fd: int, dist, group=None, timeout=60.0):
     """Hand one file descriptor per rank to every other rank of the box.  Returns a list with, for
     every peer rank, a descriptor valid in THIS process (own entry -1); the caller closes them."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    import os
     srv = _FdServer(world, timeout)
     try:
-        names = _gather(srv.name, dist, group)
-        srv.serve(my_fd)
+        pairs = _gather((srv.name, os.getpid()), dist, group)
+        names = [n for n, _ in pairs]
+        srv.serve(my_fd, allowed_pids=[p for _, p in pairs])
         fds = _receive_fds(names, rank, timeout)
     finally:
         srv.close()
@@ -140,12 +162,12 @@ def share_windows(alloc_fd, attach_fd, free_window, alloc_ipc, attach_ipc, dist,
         fds = [-1] * world
         try:
             fd = alloc_fd()
-            first = _gather((fd is not None, srv.name), dist, group)
-            if all(ok for ok, _ in first):
+            first = _gather((fd is not None, srv.name, os.getpid()), dist, group)
+            if all(ok for ok, _, _ in first):
                 ok, err = True, None
                 try:
-                    srv.serve(fd)
-                    fds = _receive_fds([name for _, name in first], rank)
+                    srv.serve(fd, allowed_pids=[p for _, _, p in first])
+                    fds = _receive_fds([name for _, name, _ in first], rank)
                     ok = bool(attach_fd(fds))
                 except Exception as e:      # socket trouble counts like an import failure
                     ok, err = False, e
@@ -198,6 +220,8 @@ def attach(des: DeviceDesign, dist, group=None, piggyback=None):
                                  alloc_ipc, attach_ipc, dist, group, piggyback,
                                  prefer_vmm=os.environ.get("FOS_COMM", "vmm") != "ipc")
     des.comm_kind = kind
+    if hasattr(des, "_life"):
+        des._life["sharded"] = world > 1      # reclaiming it without multigpu.close() warns
     return extras
 
 
@@ -239,4 +263,4 @@ def close(des: DeviceDesign, dist, group=None):
     kernels, so every rank must be done with its last solve before any window goes away:
     barrier first, then close."""
     dist.barrier(group)
-    des.close()
+    des.close()     # explicit: no ResourceWarning from the finalizer

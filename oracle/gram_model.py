@@ -68,3 +68,32 @@ def fista_gram(G, c, btb, alpha1, alpha2, L, max_iter, t_init_factor=1.0):
             obj += alpha1 * float(np.abs(x).sum())
         objs.append(obj)
     return x, objs
+
+
+def fista_gram_batch(G, c, btb, alphas1, alpha2, L, max_iter, t_init_factor=1.0):
+    """``fista_gram`` for a vector of L1 penalties at once (one column per penalty, the layout of
+    path_step_kernel): returns (X [n_lambda, d], objectives of the final iterates).  Column j is
+    elementwise the same recurrence as ``fista_gram(G, c, btb, alphas1[j], ...)``; only the matrix
+    product is batched."""
+    alphas1 = np.asarray(alphas1, dtype=np.float64)
+    d, m = G.shape[0], alphas1.size
+    tau = t_init_factor / L
+    X = np.zeros((d, m))
+    Y = np.zeros((d, m))
+    t_prev = 1.0
+    thr = tau * alphas1[None, :]
+    for _ in range(max_iter):
+        grad = G @ Y - c[:, None]
+        if alpha2 > 0:
+            grad = grad + alpha2 * Y
+        V = Y - tau * grad
+        X_new = np.where(alphas1[None, :] > 0, _soft(V, thr), V)
+        t_cur = 0.5 * (1.0 + np.sqrt(1.0 + 4.0 * t_prev * t_prev))
+        beta = (t_prev - 1.0) / t_cur
+        Y = X_new + beta * (X_new - X)
+        X, t_prev = X_new, t_cur
+    obj = 0.5 * np.einsum("ij,ij->j", X, G @ X) - c @ X + 0.5 * btb
+    if alpha2 > 0:
+        obj = obj + 0.5 * alpha2 * np.einsum("ij,ij->j", X, X)
+    obj = obj + alphas1 * np.abs(X).sum(axis=0)
+    return X.T.copy(), obj

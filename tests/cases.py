@@ -25,9 +25,9 @@ DESIGNS = {
     "odd": dict(store=False),    # 500 x 37  (odd d: padded leading dimension on device)
     "wide": dict(store=False),   # 1500 x 640 (streaming kernel, d >= 512)
     # 2000 x 64, option combinations off the figure-legend grid (restart thresholds, ratio stops with
-    # backtracking, steep / shallow Armijo factors, non-zero ISTA start, capped L-BFGS).  Pins the
-    # oracle and the host layer on the CPU; staged for the GPU suite (cpu_only) until it has run there.
-    "midx": dict(store=False, cpu_only=True),
+    # backtracking, steep / shallow Armijo factors, non-zero ISTA start, capped L-BFGS).  Runs against
+    # the oracle and the host layer on the CPU and against the kernels in the GPU suite.
+    "midx": dict(store=False),
 }
 
 

@@ -209,8 +209,21 @@ def test_metrics_contract(be):
         ls_b = list(S.ls_call_iters)
     finally:
         S.C = old
-    assert ls_a != ls_b or True   # a stricter C can only shrink more
-    assert sum(ls_b) >= sum(ls_a)
+    # the same two runs through the oracle with its Armijo constant switched the same way: the
+    # shrink counts must agree exactly, and the stricter constant shrinks strictly more here
+    import oracle
+    from oracle import ref_numpy
+    want = []
+    try:
+        for c_val in (old, 0.9):
+            ref_numpy.ARMIJO_C = c_val
+            np.random.seed(0)
+            oracle.fista(A, b, "lasso", 5.0, 0.0, backtracking=True, t_init_factor=4.0, max_iter=10)
+            want.append(list(oracle.METRICS["ls_iters"]))
+    finally:
+        ref_numpy.ARMIJO_C = old
+    assert ls_a == want[0] and ls_b == want[1]
+    assert sum(ls_b) > sum(ls_a)
     assert xa.shape == (A.shape[1],)
 
 
@@ -302,8 +315,11 @@ def test_device_lbfgs_well_conditioned():
 
 @pytest.mark.parametrize("name", ["mid", "wide", "c1"])
 def test_device_lbfgs_golden_designs(name):
-    """On the (ill-conditioned) golden designs: the first iterations match the reference's trace
-    and the converged objective agrees; in between the quasi-Newton recursion amplifies rounding."""
+    """Device L-BFGS against the reference's golden L-BFGS traces.  The bound is the one the CPU
+    model of the same algorithm meets against scipy on these designs
+    (tests/test_lbfgs_model_cpu.py::test_model_equals_scipy_on_golden_designs: identical iteration
+    counts, objective traces to 1e-10, x to 1e-9), relaxed by one order of magnitude for the
+    different summation order of the GPU gradient."""
     from fastoptsolver_b200.lbfgs import LBFGSSolver
     A, b = cases.design(name)
     g = harness.golden(name)
@@ -313,11 +329,91 @@ def test_device_lbfgs_golden_designs(name):
         dev = LBFGSSolver(spec["reg_type"], a1, a2, driver="device", **spec["kw"])
         dev.fit(A, b)
         ref_h = g[f"{key}/hobj"]
-        k = min(3, len(ref_h))
-        np.testing.assert_allclose(dev.history_[:k], ref_h[:k], rtol=1e-9)
-        assert abs(dev.history_[-1] - ref_h[-1]) <= 1e-7 * abs(ref_h[-1])
-        assert abs(len(dev.history_) - len(ref_h)) <= max(3, len(ref_h) // 4)
-        assert harness.rel_err(dev.x_, g[f"{key}/x"]) <= 1e-3
+        assert len(dev.history_) == len(ref_h), (name, key, len(dev.history_), len(ref_h))
+        err = np.abs(np.asarray(dev.history_) - ref_h) / np.abs(ref_h)
+        assert err.max() <= 1e-9, (name, key, err.max())
+        assert harness.rel_err(dev.x_, g[f"{key}/x"]) <= 1e-8, (name, key, harness.rel_err(dev.x_, g[f"{key}/x"]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("d", [1500, 2048, 3000, 4096])
+def test_streaming_builds_mid_widths(d, dtype):
+    """The streaming builds for 1024 < lda <= 4096 -- fp32 storage (256,8,4) / (256,16,2), fp64
+    (256,8,2) / (256,16,1) -- on row counts that leave partial last stages, with and without column
+    padding inside a thread's vector: gradient, objective, a fixed-step and an Armijo FISTA run
+    against the oracle.  fp32 storage is compared at the fp64 tolerance (arithmetic is fp64 on both
+    sides; north_star allows 1e-5)."""
+    import oracle
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200.design import DeviceDesign
+    rng = np.random.default_rng(d)
+    n = 1237
+    A = np.asarray(rng.standard_normal((n, d)) / np.sqrt(n), dtype=dtype)
+    A[:, ::3] *= 2.0
+    b = rng.standard_normal(n)
+    A64 = A.astype(np.float64)
+    des = DeviceDesign.from_host(A, b)
+    x = rng.standard_normal(d)
+    loss, g = des.grad(x, 0.3)
+    lr, gr = oracle.smooth_value_and_grad(x, A64, b, 0.3)
+    assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
+    assert abs(des.objective(x, 3, 0.2, 0.3) - oracle.compute_objective(x, A64, b, "elasticnet", 0.2, 0.3)) <= 1e-12 * lr
+    a1 = 0.2 * float(np.max(np.abs(A64.T @ b)))
+    for kw in (dict(), dict(backtracking=True, t_init_factor=2.0)):
+        np.random.seed(0)
+        xr, hr = oracle.fista(A64, b, "lasso", a1, 0.0, max_iter=15, return_history=True, **kw)
+        ls_ref = list(oracle.METRICS["ls_iters"])
+        np.random.seed(0)
+        xg, hg = S.fista(des, None, "lasso", a1, 0.0, max_iter=15, return_history=True, **kw)
+        assert harness.rel_err(xg, xr) <= 1e-10
+        np.testing.assert_allclose(hg["obj"], hr["obj"], rtol=1e-10)
+        assert list(S.ls_call_iters) == ls_ref
+        assert np.array_equal(xg == 0.0, xr == 0.0), "sparsity pattern differs"
+    des.close()
+
+
+@pytest.mark.parametrize("dtype,d", [(np.float32, 2048), (np.float32, 4096), (np.float64, 4096)])
+def test_streaming_ring_wraps(dtype, d):
+    """Enough rows per CTA for the shared-memory ring to wrap many times (the small cases above never
+    refill a slot): one gradient + both dots against numpy on the downloaded design."""
+    import oracle
+    from fastoptsolver_b200.design import DeviceDesign
+    n = 148 * 150 + 77
+    des = DeviceDesign.synthetic(n, d, dtype, seed=4, noise_std=1.0, rho1=0.5, rho2=0.7)
+    A, b = des.download()
+    A64 = A.astype(np.float64)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(d) * (rng.random(d) < 0.2)
+    loss, g = des.grad(x, 0.0)
+    lr, gr = oracle.smooth_value_and_grad(x, A64, b, 0.0)
+    assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
+    assert abs(des.objective(x, 1, 0.5, 0.0) - oracle.compute_objective(x, A64, b, "lasso", 0.5, 0.0)) <= 1e-12 * lr
+    des.close()
+
+
+def test_dropin_module_global_C_reaches_the_device():
+    """The reference's writable module global ``C`` (iterative_solvers.py:11), set on the DROP-IN
+    module the way a notebook would, changes the Armijo decisions taken on the device."""
+    import importlib
+    import sys
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastoptsolver_b200", "dropin")
+    sys.path.insert(0, d)
+    try:
+        sys.modules.pop("iterative_solvers", None)
+        IS = importlib.import_module("iterative_solvers")
+        A, b = cases.design("mid")
+        counts = []
+        for c_val in (1e-2, 0.9):
+            IS.C = c_val
+            np.random.seed(0)
+            IS.fista(A, b, "lasso", 5.0, 0.0, backtracking=True, t_init_factor=4.0, max_iter=10)
+            counts.append(list(IS.ls_call_iters))
+        IS.C = 1e-2
+        assert counts[0][0] == 1 and counts[1][0] == 4, counts      # reference values (oracle run)
+    finally:
+        IS.C = 1e-2
+        sys.path.remove(d)
+        sys.modules.pop("iterative_solvers", None)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -340,31 +436,59 @@ def test_device_standardize(dtype):
 
 
 def test_design_cache_semantics():
-    """numpy inputs are re-used only while they are the same, unchanged objects."""
+    """Default: bare numpy inputs are uploaded on every call (the reference re-reads them), so an
+    in-place edit between two calls is always seen.  Opt-in cache: reuse only while the arrays are
+    the same, unchanged objects."""
+    import oracle
     from fastoptsolver_b200 import design as D
+    from fastoptsolver_b200 import iterative_solvers as S
     rng = np.random.default_rng(0)
     A = rng.standard_normal((300, 24))
     b = rng.standard_normal(300)
     D.clear_cache()
-    d1 = D.as_design(A, b)
-    assert D.as_design(A, b) is d1                      # same objects, same content: reuse
-    b[5] += 1.0                                         # b is fully fingerprinted
-    d2 = D.as_design(A, b)
-    assert d2 is not d1
-    A[0, 3] = 7.0                                       # first / last rows are fingerprinted
-    d3 = D.as_design(A, b)
-    assert d3 is not d2
-    A2 = A.copy()                                       # equal content, different object: upload again
-    assert D.as_design(A2, b) is not d3
-    loss, g = d3.grad(np.ones(24))
-    import oracle
-    lr, gr = oracle.smooth_value_and_grad(np.ones(24), A, b)
-    assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
-    with pytest.raises(ValueError):
-        d3.grad(np.ones(5))
+    D.set_cache(None)
+    assert not D.cache_enabled()
+    # drop-in behaviour: edit a feature in place between two calls -> second call sees it
+    np.random.seed(0)
+    x1 = S.fista(A, b, "lasso", 1.0, 0.0, max_iter=10)
+    A[:, 7] *= 0.25
+    np.random.seed(0)
+    x2 = S.fista(A, b, "lasso", 1.0, 0.0, max_iter=10)
+    np.random.seed(0)
+    x2_ref = oracle.fista(A, b, "lasso", 1.0, 0.0, max_iter=10)
+    assert harness.rel_err(x2, x2_ref) <= 1e-10 and not np.array_equal(x1, x2)
+    try:
+        D.set_cache(True)
+        d1 = D.as_design(A, b)
+        assert D.as_design(A, b) is d1                      # same objects, same content: reuse
+        b[5] += 1.0                                         # b is fully fingerprinted
+        d2 = D.as_design(A, b)
+        assert d2 is not d1
+        A[17, 3] = 7.0                                      # small matrices are hashed completely
+        d3 = D.as_design(A, b)
+        assert d3 is not d2
+        A2 = A.copy()                                       # equal content, different object: upload again
+        assert D.as_design(A2, b) is not d3
+        loss, g = d3.grad(np.ones(24))
+        lr, gr = oracle.smooth_value_and_grad(np.ones(24), A, b)
+        assert abs(loss - lr) <= 1e-12 * lr and harness.rel_err(g, gr) <= 1e-12
+        with pytest.raises(ValueError):
+            d3.grad(np.ones(5))
+        # a large matrix (sampled fingerprint): a column edit and a sparse row edit are both caught
+        big = rng.standard_normal((1 << 16, 64))
+        bb = rng.standard_normal(1 << 16)
+        e1 = D.as_design(big, bb)
+        assert D.as_design(big, bb) is e1
+        big[:, 33] = 0.0
+        e2 = D.as_design(big, bb)
+        assert e2 is not e1
+        big[1000:9000] += 1.0
+        assert any(D.as_design(big, bb) is not e2 for _ in range(20))
+    finally:
+        D.set_cache(None)
+        D.clear_cache()
     with pytest.raises(NotImplementedError):
         D.DeviceDesign.from_host(np.zeros((4, 9000)), np.zeros(4))
-    D.clear_cache()
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

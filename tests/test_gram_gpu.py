@@ -129,3 +129,42 @@ def test_warm_started_path_matches_cold_batch():
     assert sum(iw["iters"]) > 0 and len(iw["iters"]) == 3
     gram.close()
     des.close()
+
+
+def test_gram_and_path_at_config5_width():
+    """d = 4096, 256 penalties -- the column count and penalty count of BASELINE config 5 (the
+    7-split SYRK and the 128 x 64 path tiles at their real shape) on 20 000 rows: G, c, b.b against
+    numpy; every one of the 256 columns against the numpy model of the Gram recurrence
+    (oracle/gram_model.py, itself pinned to the reference formulation in tests/test_gram_model_cpu.py);
+    three columns against the reference formulation (oracle.fista on A) directly."""
+    import oracle
+    from oracle import gram_model
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    n, d, n_lam, iters = 20000, 4096, 256, 40
+    des = DeviceDesign.synthetic(n, d, seed=2, noise_std=0.5, rho1=0.5, rho2=0.7)
+    des.standardize()
+    A, b = des.download()
+    gram = GM.GramDesign(des)
+    G, c = gram.download()
+    G_ref = A.T @ A
+    assert harness.rel_err(G, G_ref) <= 1e-13
+    assert np.array_equal(G, G.T)
+    assert harness.rel_err(c, A.T @ b) <= 1e-13 and abs(gram.btb - b @ b) <= 1e-13 * (b @ b)
+    lam = float(np.max(np.abs(c)))
+    alphas = lam * np.logspace(0, -3, n_lam)
+    L = float(np.linalg.eigvalsh(G_ref)[-1]) * 1.0001
+    X, info = GM.fista_path(des, None, alphas, max_iter=iters, L=L, gram=gram)
+    assert info["iters"] == iters and X.shape == (n_lam, d)
+    X_ref, obj_ref = gram_model.fista_gram_batch(G_ref, A.T @ b, float(b @ b), alphas, 0.0, L, iters)
+    scale = np.linalg.norm(X_ref[-1])
+    for j in range(n_lam):
+        assert np.linalg.norm(X[j] - X_ref[j]) <= 1e-9 * max(np.linalg.norm(X_ref[j]), 1e-3 * scale), j
+        assert abs(info["obj"][j] - obj_ref[j]) <= 1e-9 * abs(obj_ref[j]), j
+    assert np.array_equal(X == 0.0, X_ref == 0.0) or np.mean((X == 0.0) != (X_ref == 0.0)) < 1e-6
+    for j in (3, 128, 255):
+        x_ref, h = _oracle_fista_fixed_L(oracle, A, b, alphas[j], 0.0, L, iters)
+        assert harness.rel_err(X[j], x_ref) <= 1e-9
+        assert abs(info["obj"][j] - h[-1]) <= 1e-9 * abs(h[-1])
+    gram.close()
+    des.close()

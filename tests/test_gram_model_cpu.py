@@ -78,3 +78,21 @@ def test_fista_on_gram_equals_reference(a2_frac):
         tie = 1e-6 * max(np.abs(x_ref).max(), 1e-300)
         big = np.abs(x_ref) > tie
         assert np.array_equal(np.sign(x[big]), np.sign(x_ref[big]))
+
+
+def test_batched_model_equals_per_column_model():
+    """fista_gram_batch (used by the GPU test at the config-5 shape) == fista_gram column by column."""
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((400, 48))
+    A[:, 1:] += 0.4 * A[:, :-1]
+    b = A @ np.where(np.arange(48) % 6 == 0, 1.0, 0.0) + 0.2 * rng.standard_normal(400)
+    G, c, btb = GM.gram(A, b)
+    lam = float(np.max(np.abs(c)))
+    alphas = lam * np.array([1.2, 0.5, 0.1, 0.01, 0.0])
+    L = float(np.linalg.eigvalsh(G)[-1])
+    for a2 in (0.0, 0.3):
+        X, obj = GM.fista_gram_batch(G, c, btb, alphas, a2, L + a2, 40)
+        for j, a1 in enumerate(alphas):
+            x, objs = GM.fista_gram(G, c, btb, a1, a2, L + a2, 40)
+            assert np.linalg.norm(X[j] - x) <= 1e-13 * max(np.linalg.norm(x), 1.0)
+            assert abs(obj[j] - objs[-1]) <= 1e-12 * abs(objs[-1])

@@ -149,3 +149,44 @@ def test_world3_gloo():
         p.join(timeout=60)
     assert [r[1] for r in res] == ["ok"] * 3, res
     assert [r[2] for r in res] == [(0, 333), (333, 667), (667, 1001)]
+
+
+def test_descriptor_server_only_serves_the_announced_ranks():
+    """The abstract-namespace socket is visible to every local process.  A connection that does not
+    come from one of the announced process ids (SO_PEERCRED) gets no descriptor and does not use up a
+    hand-over; an announced one does."""
+    import subprocess
+    import warnings
+    sys.path.insert(0, ROOT)
+    from fastoptsolver_b200 import multigpu
+    rd, wr = os.pipe()
+    srv = multigpu._FdServer(world=2, timeout=20.0)
+    try:
+        srv.serve(rd, allowed_pids=[os.getpid()])
+        # an intruder: another process of the same user connecting first
+        code = ("import socket,sys\n"
+                "c=socket.socket(socket.AF_UNIX,socket.SOCK_STREAM);c.settimeout(10)\n"
+                f"c.connect({srv.name!r})\n"
+                "m,f,_,_=socket.recv_fds(c,16,1)\n"
+                "print(len(f))\n")
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+        assert out.stdout.strip() == "0", out
+        # the announced rank (this process) still gets its descriptor
+        fds = multigpu._receive_fds([srv.name, "unused"], rank=1, timeout=10.0)
+        assert fds[0] >= 0 and fds[1] == -1
+        os.write(wr, b"k")
+        assert os.read(fds[0], 1) == b"k"
+        os.close(fds[0])
+    finally:
+        srv.close()
+        os.close(rd)
+        os.close(wr)
+    assert len(srv.rejected) == 1 and not srv.errors
+    # a sharded design reclaimed by the garbage collector (no barrier) warns; an explicit close does not
+    from fastoptsolver_b200 import design as D
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        D._destroy(0, {"sharded": True, "explicit": True})
+        assert not w
+        D._destroy(0, {"sharded": True, "explicit": False})
+        assert len(w) == 1 and issubclass(w[0].category, ResourceWarning)
