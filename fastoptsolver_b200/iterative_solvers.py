@@ -250,6 +250,9 @@ def fista(
     t0 = time.perf_counter()
     des = as_design(A, b)
     t1 = time.perf_counter()
+    if des is not A:      # uploaded (or found) by this call: what the upload did (include/fos.h, fos_design_upload_gram)
+        ug = des.upload_gram()
+        last_run["upload_gram"] = {"state": ug["state"], "copy_ms": ug["copy_ms"], "tail_ms": ug["tail_ms"]}
     L_val = estimate_lipschitz(des)
     t2 = time.perf_counter()
     if alpha2 > 0:

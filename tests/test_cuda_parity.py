@@ -555,3 +555,26 @@ def test_full_size_properties_1Mx4096():
         assert abs(full.objective(xi, 1, a1, 0.0) - oi) <= 1e-12 * abs(oi)
     assert h["obj"][-1] < h["obj"][0]
     full.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_generator_matches_numpy_model(dtype):
+    """csrc/datagen.cu (Philox4x32-10 keyed by (row, group, draw), Box-Muller, the reference's
+    5-column recipe) against its independent numpy restatement (oracle/datagen_model.py), which
+    `bench.py --impl reference` uses to build the same design without the product.  Agreement is to
+    rounding (CUDA's log / sincospi vs numpy's log / sin / cos), for any row offset."""
+    from oracle import datagen_model
+    from fastoptsolver_b200.design import DeviceDesign
+    sc = dict(seed=(7 << 32) | 12345, noise_std=0.5, rho1=0.5, rho2=0.7)
+    for n, d, row0 in ((513, 37, 0), (300, 640, 10_000_000_000), (64, 4, 5)):
+        des = DeviceDesign.synthetic(n, d, dtype, row0=row0, **sc)
+        A, b = des.download()
+        A_ref, b_ref = datagen_model.synth_rows(n, d, row0=row0, dtype=dtype, threads=1, **sc)
+        tol = 1e-13 if dtype == np.float64 else 2e-7
+        assert np.max(np.abs(A.astype(np.float64) - A_ref.astype(np.float64))) <= tol * 8.0
+        np.testing.assert_allclose(b, b_ref, rtol=0, atol=(1e-11 if dtype == np.float64 else 1e-4) * max(1.0, np.abs(b_ref).max()))
+        des.close()
+    # the virtual design is row-addressable: a shard generated at an offset equals those rows of the whole
+    whole, _ = datagen_model.synth_rows(100, 20, row0=0, threads=1, **sc)
+    part, _ = datagen_model.synth_rows(30, 20, row0=50, threads=1, **sc)
+    assert np.array_equal(whole[50:80], part)
