@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--cols", type=int, default=4096)
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--reps", type=int, default=60)
+    ap.add_argument("--modes", default="probe,grad,grad+dot2,dot2")
     args = ap.parse_args()
     dt = np.float64 if args.dtype == "f64" else np.float32
     des = DeviceDesign.synthetic(args.rows, args.cols, dt, seed=0)
@@ -66,6 +67,8 @@ def main():
     nbytes = args.rows * args.cols * np.dtype(dt).itemsize + args.rows * 8
     out = {"rows": args.rows, "cols": args.cols, "dtype": args.dtype, "bytes": nbytes, "runs": []}
     for name, mode in (("probe", 8), ("grad", 1), ("grad+dot2", 3), ("dot2", 2)):
+        if name not in args.modes.split(","):
+            continue
         for reps in (2, args.reps):
             ms = C.c_float()
             time.sleep(1.0)
