@@ -100,6 +100,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first_sample(self, timeout=3.0):
+        """Return once nvidia-smi has delivered its first row: its start-up (NVML initialisation, a
+        fresh process attaching to the GPU) takes 0.1-0.3 s and measurably slows kernels that run
+        meanwhile (r2: 197 it/s in a timed region that overlapped it, 213-224 it/s for the identical
+        solves that followed), so it must be over before the timed region begins."""
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+        self.t0 = time.perf_counter()
+
     def elapsed(self):
         return time.perf_counter() - self.t0 if self.t0 else 0.0
 
@@ -417,11 +427,13 @@ def bench_fista(ctx, cfg_name):
             adaptive_restart=False, restart_threshold=1.0, want_history=True)
         return x, oh[:it], dict(S.last_run["solver"])
 
-    solve(W, False)                                   # warm-up steps (untimed)
-    ctx.barrier()
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    ctx.barrier()
+    solve(W, False)                                   # warm-up steps (untimed)
+    ctx.barrier()
     x, obj, info = solve(K, False)                    # EXACTLY K timed steps
     ctx.barrier()
     # Same K steps once more with a CUDA-event pair around every gradient-kernel launch (on the
@@ -436,7 +448,7 @@ def bench_fista(ctx, cfg_name):
     for _ in range(n_soak):
         soak_ms.append(solve(K, False)[2]["loop_ms"])
     ctx.barrier()
-    clocks = sampler.stop(covers=["timed K steps", "event-timed repeat", f"{n_soak} x K soak steps"]) if rank == 0 else None
+    clocks = sampler.stop(covers=["warm-up steps", "timed K steps", "event-timed repeat", f"{n_soak} x K soak steps"]) if rank == 0 else None
     loop_ms = ctx.max_over_ranks(info["loop_ms"])
     per_rank = None
     if dist is not None:
@@ -615,12 +627,14 @@ def bench_lbfgs(ctx):
         sol.fit(des)
         return sol, dict(S.last_run["lbfgs"])
 
-    for _ in range(W):
-        fit()
-    ctx.barrier()
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    ctx.barrier()
+    for _ in range(W):
+        fit()
+    ctx.barrier()
     fg = 0
     loop_ms = 0.0
     iters = 0
@@ -640,7 +654,7 @@ def bench_lbfgs(ctx):
     for _ in range(soak):
         fit()
     ctx.barrier()
-    clocks = sampler.stop(covers=["timed K fits", f"{reps} event-timed gradient launches", f"{soak} soak fits"]) \
+    clocks = sampler.stop(covers=["warm-up fits", "timed K fits", f"{reps} event-timed gradient launches", f"{soak} soak fits"]) \
         if rank == 0 else None
     loop_ms = ctx.max_over_ranks(loop_ms)
     value = fg / (loop_ms * 1e-3)
@@ -669,7 +683,7 @@ def bench_lbfgs(ctx):
     if not args.no_e2e:
         out["e2e"] = e2e_lbfgs(ctx, des, a1, a2, K)
     if rank == 0 and world == 1 and not args.no_cpu:
-        rows_s = pick_sample_rows(rows_gpu, d, args.cpu_sample_rows) // 2     # numpy up-casts A per product: keep it small
+        rows_s = pick_sample_rows(rows_gpu, d, args.cpu_sample_rows) // 8     # numpy up-casts A per product: keep it small
         A_s, b_s = des.download(0, rows_s)
         out["cpu_baseline"] = cpu_lbfgs_sample(A_s, b_s, a1 * rows_s / rows_gpu, a2 * rows_s / rows_gpu, rows_gpu / rows_s)
     if rank == 0:
@@ -773,18 +787,20 @@ def bench_path(ctx):
     Lm = len(alphas)
     np.random.seed(0)
     L = S.estimate_lipschitz(des)
-    GM.fista_path(des, None, alphas, max_iter=W, L=L, gram=gram)        # warm-up steps
-    ctx.barrier()
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    ctx.barrier()
+    GM.fista_path(des, None, alphas, max_iter=W, L=L, gram=gram)        # warm-up steps
+    ctx.barrier()
     X, info = GM.fista_path(des, None, alphas, max_iter=K, L=L, gram=gram)   # EXACTLY K timed steps
     ctx.barrier()
     soak = soak_rounds(ctx, sampler, 1e-3 * info["loop_ms"] + 5e-3, cap=200)
     for _ in range(soak):
         GM.fista_path(des, None, alphas, max_iter=K, L=L, gram=gram)
     ctx.barrier()
-    clocks = sampler.stop(covers=["timed K path iterations", f"{soak} x K soak iterations"]) if rank == 0 else None
+    clocks = sampler.stop(covers=["warm-up iterations", "timed K path iterations", f"{soak} x K soak iterations"]) if rank == 0 else None
     loop_ms = ctx.max_over_ranks(info["loop_ms"])
     rows_local = des.shape[0]
     tiles = d // 128 if d % 128 == 0 else (d + 127) // 128
@@ -905,7 +921,7 @@ def reference_arm(ctx):
         extra = {"gradient_only_it_s": res["grad_it_s"], "whole_call_it_s": res["call_it_s"],
                  "lipschitz_s": res["lipschitz_s"]}
     elif cfg == "c4":
-        rows_s = pick_sample_rows(n, d, args.cpu_sample_rows) // 2
+        rows_s = pick_sample_rows(n, d, args.cpu_sample_rows) // 8
         A_s, b_s = datagen_model.synth_rows(rows_s, d, dtype=np.float32, **SCENARIO)
         lam_s = float(np.max(np.abs(A_s.astype(np.float64).T @ b_s)))
         base = cpu_lbfgs_sample(A_s, b_s, ALPHA_FRAC * lam_s, ALPHA_FRAC * lam_s, n / rows_s)

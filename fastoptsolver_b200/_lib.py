@@ -127,6 +127,8 @@ SIGNATURES = {
     "fos_gram_pointers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "fos_gram_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fos_gram_set_btb": (C.c_int, [C.c_void_p, C.c_double]),
+    "fos_gram_subset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "fos_gram_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fos_gram_path_fista": (C.c_int, [C.c_void_p, C.POINTER(PathParams), C.POINTER(PathResult)]),
 }
 

@@ -306,11 +306,13 @@ int fos_balance_rows(fos_design* h) {
 }
 
 
+static void blk_give(int device, void* p, size_t cap);  // matrix-block recycling, below
+
 static void design_free(fos_design* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->owns_A && h->A) cudaFree(h->A);
+    if (h->owns_A && h->A) blk_give(h->device, h->A, h->A_cap);
     if (h->owns_b && h->b) cudaFree(h->b);
     fos_upload_gram_drop(h);
     void* bufs[] = {h->work_block, h->sm_slot, h->arena};
@@ -345,9 +347,70 @@ static void design_free(fos_design* h) {
 // for an 8 GB shard with 3 peers, once: the driver then reuses the freed block in 2-25 ms).  The
 // stream-ordered pool (cudaMallocAsync) avoids the peer mapping but pays 300-540 ms for the same
 // 8 GB on EVERY allocation (tools/exp_e2e_multi.py), so it is not used.
+// The reference re-reads its arrays on every call, so a drop-in caller uploads the same design again
+// and again (19 solver variants per scenario in the notebook).  A fresh cudaMalloc of a large block
+// and the cudaFree that follows cost far more than they look (page tables for tens of GB: measured
+// ~0.2 s of a 0.8 s upload of 32.8 GB), so the matrix block of a destroyed design is kept -- one
+// block per device, >= 256 MB -- and handed to the next design that fits in it.  fos_trim() releases
+// it; FOS_KEEP_BLOCK=0 switches the cache off.
+static std::mutex g_blk_mu;
+static std::map<int, std::pair<void*, size_t>> g_blk_cache;  // device -> (block, bytes), not in use
+constexpr size_t FOS_BLOCK_CACHE_MIN = 256u << 20;
+
+static bool blk_cache_on() {
+    const char* e = getenv("FOS_KEEP_BLOCK");
+    return !(e && e[0] == '0');
+}
+
+static void* blk_take(int device, size_t bytes, size_t* cap) {
+    std::lock_guard<std::mutex> lock(g_blk_mu);
+    auto it = g_blk_cache.find(device);
+    if (it == g_blk_cache.end()) return nullptr;
+    void* p = it->second.first;
+    const size_t have = it->second.second;
+    g_blk_cache.erase(it);
+    if (have >= bytes) {
+        *cap = have;
+        return p;
+    }
+    cudaFree(p);  // too small for the newcomer: make room before the fresh allocation
+    return nullptr;
+}
+
+static void blk_give(int device, void* p, size_t cap) {
+    if (!p) return;
+    if (!blk_cache_on() || cap < FOS_BLOCK_CACHE_MIN) {
+        cudaFree(p);
+        return;
+    }
+    std::lock_guard<std::mutex> lock(g_blk_mu);
+    auto it = g_blk_cache.find(device);
+    if (it != g_blk_cache.end()) {
+        if (it->second.second >= cap) {  // keep the larger one
+            cudaFree(p);
+            return;
+        }
+        cudaFree(it->second.first);
+        g_blk_cache.erase(it);
+    }
+    g_blk_cache[device] = std::make_pair(p, cap);
+}
+
+void fos_block_cache_trim() {
+    std::lock_guard<std::mutex> lock(g_blk_mu);
+    for (auto& kv : g_blk_cache) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.first);
+    }
+    g_blk_cache.clear();
+    cudaGetLastError();
+}
+
 static int alloc_matrix(fos_design* h) {
     const size_t bytes = static_cast<size_t>(h->n) * h->lda * elem_size(h->dtype);
-    cudaError_t e = cudaMalloc(&h->A, bytes);
+    h->A_cap = bytes;
+    h->A = blk_take(h->device, bytes, &h->A_cap);
+    cudaError_t e = h->A ? cudaSuccess : cudaMalloc(&h->A, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         fos_set_error("cannot allocate %.2f GB of HBM for A (%lld x %d)", bytes / 1e9, h->n, h->d);

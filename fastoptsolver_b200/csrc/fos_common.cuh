@@ -164,6 +164,7 @@ struct fos_design {
     int d = 0, lda = 0, ldv = 0;
     int dtype = FOS_F64;
     void* A = nullptr;
+    size_t A_cap = 0;  // bytes of the block A sits in (>= the matrix: blocks are recycled, fos_api.cu)
     double* b = nullptr;
     bool owns_A = false, owns_b = false;
     // workspaces (carved out of work_block / pin_block)
@@ -231,6 +232,7 @@ int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hi
                         double a2, int bits);
 int fos_grad_plan(fos_design* h);
 void fos_comm_vmm_release(fos_design* h);
+void fos_block_cache_trim();  // releases the recycled matrix blocks (part of fos_trim)
 int fos_comm_after_attach(fos_design* h);  // common tail of the attach variants (row-balance policy)
 int fos_balance_rows(fos_design* h);  // SM-indexed row partition weighted by measured per-SM rates  // picks kernel + n_parts, sets smem attributes
 int fos_launch_prox(const double* v_dev, double* out_dev, long long len, double thresh,

@@ -411,6 +411,43 @@ __global__ void __launch_bounds__(1024) gram_power_finish_kernel(const double* _
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Strong-rule screening (gram.py: fista_path_screened): the Gram system restricted to a feature
+// subset, G_S[i][j] = G[idx[i]][idx[j]], zero padded to the tile width (a padded feature has a zero
+// row, a zero c entry and therefore stays at 0).
+__global__ void gram_gather_kernel(const double* __restrict__ G, const double* __restrict__ c, int d,
+                                   const int* __restrict__ idx, int n_idx, int dsub, double* __restrict__ Gs,
+                                   double* __restrict__ cs) {
+    const int i = blockIdx.y;
+    const int si = (i < n_idx) ? idx[i] : -1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < dsub; j += gridDim.x * blockDim.x) {
+        const int sj = (j < n_idx) ? idx[j] : -1;
+        Gs[static_cast<size_t>(i) * dsub + j] = (si >= 0 && sj >= 0) ? G[static_cast<size_t>(si) * d + sj] : 0.0;
+        if (i == 0) cs[j] = (sj >= 0) ? c[sj] : 0.0;
+    }
+}
+
+// out[l][i] = (G x_l)[i] - c[i]: gradient of the smooth part (without the alpha2 term) for n_cols
+// columns; one warp per (row, column).  Used for the strong rule and its KKT re-check.
+__global__ void __launch_bounds__(256) gram_apply_kernel(const double* __restrict__ G, const double* __restrict__ c,
+                                                         const double* __restrict__ X, double* __restrict__ out, int d) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d) return;
+    const double2* g2 = reinterpret_cast<const double2*>(G + static_cast<size_t>(row) * d);
+    const double2* v2 = reinterpret_cast<const double2*>(X + static_cast<size_t>(blockIdx.y) * d);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const int n2 = d / 2;
+    for (int q = lane; q < n2; q += 64) {
+        const double2 a0 = g2[q], a1 = g2[q + 32];
+        const double2 x0 = v2[q], x1 = v2[q + 32];
+        s[0] = fma(a0.x, x0.x, s[0]);
+        s[1] = fma(a0.y, x0.y, s[1]);
+        s[2] = fma(a1.x, x1.x, s[2]);
+        s[3] = fma(a1.y, x1.y, s[3]);
+    }
+    const double t = fos_warp_sum((s[0] + s[1]) + (s[2] + s[3]));
+    if (lane == 0) out[static_cast<size_t>(blockIdx.y) * d + row] = t - c[row];
+}
+
 struct fos_gram {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -512,6 +549,7 @@ extern "C" int fos_trim(void) {
     }
     g_ws_cache.clear();
     cudaGetLastError();
+    fos_block_cache_trim();
     return FOS_OK;
 }
 
@@ -817,6 +855,68 @@ extern "C" int fos_gram_download(fos_gram* g, double* G_out, double* c_out) {
 }
 
 // replace G and c (after an all-reduce over row-sharded ranks done by the caller)
+extern "C" int fos_gram_subset(fos_gram* g, const int* idx, int n_idx, fos_gram** out) {
+    FOS_REQUIRE(g && idx && out, "null pointer argument");
+    FOS_REQUIRE(n_idx >= 1 && n_idx <= g->d, "subset size %d out of range (1..%d)", n_idx, g->d);
+    for (int i = 0; i < n_idx; ++i)
+        FOS_REQUIRE(idx[i] >= 0 && idx[i] < g->d && (i == 0 || idx[i] > idx[i - 1]),
+                    "subset indices must be strictly increasing and lie in [0, %d)", g->d);
+    FOS_CUDA(cudaSetDevice(g->device));
+    fos_gram* s = new fos_gram();
+    s->device = g->device;
+    s->d = (n_idx + GT - 1) / GT * GT;
+    s->bb = g->bb;
+    s->nsplit = 0;
+    int* idx_dev = nullptr;
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        FOS_CUDA(cudaEventCreate(&s->ev0));
+        FOS_CUDA(cudaEventCreate(&s->ev1));
+        FOS_CUDA(cudaMalloc(&s->G, static_cast<size_t>(s->d) * s->d * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&s->c, static_cast<size_t>(s->d) * sizeof(double)));
+        FOS_CUDA(cudaMalloc(&idx_dev, static_cast<size_t>(n_idx) * sizeof(int)));
+        FOS_CUDA(cudaMemcpyAsync(idx_dev, idx, static_cast<size_t>(n_idx) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        FOS_CUDA(cudaStreamSynchronize(g->stream));  // the parent matrix is complete
+        FOS_CUDA(cudaEventRecord(s->ev0, s->stream));
+        gram_gather_kernel<<<dim3(static_cast<unsigned>((s->d + 255) / 256), static_cast<unsigned>(s->d)), dim3(256), 0,
+                             s->stream>>>(g->G, g->c, g->d, idx_dev, n_idx, s->d, s->G, s->c);
+        FOS_CUDA(cudaGetLastError());
+        FOS_CUDA(cudaEventRecord(s->ev1, s->stream));
+        FOS_CUDA(cudaStreamSynchronize(s->stream));
+        FOS_CUDA(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+        return FOS_OK;
+    };
+    const int st = body();
+    if (idx_dev) cudaFree(idx_dev);
+    if (st != FOS_OK) {
+        gram_free(s);
+        return st;
+    }
+    *out = s;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* out) {
+    FOS_REQUIRE(g && X && out, "null pointer argument");
+    FOS_REQUIRE(n_cols >= 1 && n_cols <= 65535, "n_cols out of range");
+    FOS_CUDA(cudaSetDevice(g->device));
+    const size_t bytes = static_cast<size_t>(n_cols) * g->d * sizeof(double);
+    double* buf = nullptr;
+    FOS_CUDA(cudaMalloc(&buf, 2 * bytes));
+    auto body = [&]() -> int {
+        FOS_CUDA(cudaMemcpyAsync(buf, X, bytes, cudaMemcpyHostToDevice, g->stream));
+        gram_apply_kernel<<<dim3(static_cast<unsigned>((g->d + 7) / 8), static_cast<unsigned>(n_cols)), dim3(256), 0,
+                            g->stream>>>(g->G, g->c, buf, buf + static_cast<size_t>(n_cols) * g->d, g->d);
+        FOS_CUDA(cudaGetLastError());
+        FOS_CUDA(cudaMemcpyAsync(out, buf + static_cast<size_t>(n_cols) * g->d, bytes, cudaMemcpyDeviceToHost, g->stream));
+        FOS_CUDA(cudaStreamSynchronize(g->stream));
+        return FOS_OK;
+    };
+    const int st = body();
+    cudaFree(buf);
+    return st;
+}
+
 extern "C" int fos_gram_set_btb(fos_gram* g, double btb) {
     FOS_REQUIRE(g, "null gram handle");
     g->bb = btb;

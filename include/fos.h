@@ -67,8 +67,11 @@ const char* fos_last_error(void);
 int fos_device_count(void);
 /* sm_count, total/free HBM bytes of `device` */
 int fos_device_info(int device, int* sm_count, size_t* total_bytes, size_t* free_bytes);
-/* release device memory the library keeps between calls (the split workspace of the upload-time
- * Gram accumulation, up to 1.5 GB per device) */
+/* release device memory the library keeps between calls: the split workspace of the upload-time
+ * Gram accumulation (up to 1.5 GB per device) and the recycled matrix block -- the HBM block of the
+ * last destroyed design (one per device, >= 256 MB), kept because the reference's callers upload the
+ * same design again on every solver call (iterative_solvers.py:133-134 re-reads A) and a fresh
+ * allocation + free of tens of GB costs ~0.2 s; FOS_KEEP_BLOCK=0 disables the recycling */
 int fos_trim(void);
 
 /* ---- design: A (n x d) and b (n) resident on one GPU ---------------------------------
@@ -262,6 +265,16 @@ int fos_gram_info(const fos_gram* g, int* d, double* btb, float* build_ms, int* 
 int fos_gram_pointers(fos_gram* g, double** G_dev, double** c_dev);
 int fos_gram_download(fos_gram* g, double* G_out, double* c_out);
 int fos_gram_set_btb(fos_gram* g, double btb);
+/* Strong-rule screening on the regularisation path (the per-column
+ * semantics stay those of fista, iterative_solvers.py:199-221).
+ * fos_gram_subset: the Gram system restricted to the strictly increasing feature indices idx[0..n_idx):
+ *   G_S = G[idx][:, idx], c_S = c[idx], zero padded to a multiple of 128 columns (padded features stay 0);
+ *   b^T b is inherited, so objectives of the restricted problem equal those of the full problem at x_{S^c} = 0.
+ * fos_gram_apply: out[l] = G X[l] - c for n_cols host vectors of length d (row-major n_cols x d): the gradient of
+ *   the smooth part A^T(A x - b) (iterative_solvers.py:173) without the alpha2 term -- the quantity the strong
+ *   rule thresholds and the KKT re-check bounds by alpha1. */
+int fos_gram_subset(fos_gram* g, const int* idx, int n_idx, fos_gram** out);
+int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* out);
 typedef struct fos_path_params {
     const double* alphas1; /* n_lambda L1 weights */
     int n_lambda;

@@ -168,3 +168,47 @@ def test_gram_and_path_at_config5_width():
         assert abs(info["obj"][j] - h[-1]) <= 1e-9 * abs(h[-1])
     gram.close()
     des.close()
+
+
+def test_screened_path_matches_unscreened_on_device():
+    """Strong-rule screening on the device path (fos_gram_subset / fos_gram_apply + the batched
+    kernel on the kept features): every column equals the unscreened warm-started path to 1e-9, the
+    rule discards most features for the large penalties, and an over-aggressive rule is repaired by
+    the KKT re-check."""
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    import oracle
+    A, b = _design(4000, 512, 7)
+    lam = float(np.max(np.abs(A.T @ b)))
+    alphas = lam * np.logspace(-0.02, -2.0, 40)
+    np.random.seed(0)
+    L = oracle.estimate_lipschitz(A)
+    des = DeviceDesign.from_host(A, b)
+    gram = GM.GramDesign(des)
+    # building blocks against numpy
+    idx = np.array([0, 3, 4, 100, 257, 511])
+    sub = gram.subset(idx)
+    Gs, cs = sub.download()
+    G, c = gram.download()
+    assert sub.d == 128 and np.array_equal(Gs[:6, :6], G[np.ix_(idx, idx)]) and np.array_equal(cs[:6], c[idx])
+    assert not Gs[6:].any() and not Gs[:, 6:].any() and not cs[6:].any() and sub.btb == gram.btb
+    sub.close()
+    Xp = np.random.default_rng(1).standard_normal((3, 512))
+    assert harness.rel_err(gram.apply(Xp), Xp @ G - c) <= 1e-13
+    with pytest.raises(ValueError):
+        gram.subset(np.array([5, 5]))
+    # the path
+    Xw, iw = GM.fista_path_warm(des, None, alphas, chunk=8, tol=1e-11, L=L, gram=gram, max_iter=20000)
+    Xs, isc = GM.fista_path_screened(des, None, alphas, chunk=8, tol=1e-11, L=L, gram=gram, max_iter=20000)
+    scale = np.linalg.norm(Xw[-1])
+    for j in range(len(alphas)):
+        assert np.linalg.norm(Xs[j] - Xw[j]) <= 1e-9 * max(np.linalg.norm(Xw[j]), 1e-3 * scale), j
+    np.testing.assert_allclose(isc["obj"], iw["obj"], rtol=1e-10)
+    assert isc["kept"][0] < 512 // 4 and min(isc["kept"]) < 512 // 2
+    Xa, ia = GM.fista_path_screened(des, None, alphas, chunk=8, tol=1e-11, L=L, gram=gram, max_iter=20000,
+                                    rule_scale=8.0)
+    assert sum(ia["violations"]) > 0 and max(ia["kkt_rounds"]) > 1
+    for j in range(len(alphas)):
+        assert np.linalg.norm(Xa[j] - Xw[j]) <= 1e-9 * max(np.linalg.norm(Xw[j]), 1e-3 * scale), j
+    gram.close()
+    des.close()
