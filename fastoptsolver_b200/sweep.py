@@ -8,8 +8,13 @@ section 4).  This module reproduces that sweep through the drop-in API on a desi
 in HBM and writes the suboptimality traces as CSV (matplotlib is not in the image).
 
     python -m fastoptsolver_b200.sweep --n 100000 --d 2048 --out sweep_out [--scenarios 4]
+    python -m fastoptsolver_b200.sweep --source reference --n 1000 --d 5 --out sweep_c1   # the figures' own shape
 
-Every scenario uploads / generates A once; the ~19 solver variants reuse it.
+Every scenario uploads / generates A once; the ~19 solver variants reuse it.  ``--source reference``
+builds the data with the reference's generator (easy_boston_data.py:7-45, reproduced bit for bit by
+datagen.generate_correlated_design) and z-scores it on the host like the notebook did; the default
+generates the scenario in HBM (csrc/datagen.cu).  The summary records, per curve, the first
+iteration whose suboptimality is below 1e-5 -- the quantity one reads off figures/*.png.
 """
 from __future__ import annotations
 
@@ -103,6 +108,17 @@ def suboptimality(traces):
             for p, panel in traces.items()}
 
 
+def first_below(sub, level=1e-5):
+    """{panel: {curve: first iteration (1-based) with suboptimality < level, or None}}."""
+    out = {}
+    for panel, curves in sub.items():
+        out[panel] = {}
+        for label, tr in curves.items():
+            hit = next((k for k, v in enumerate(tr, start=1) if v < level), None)
+            out[panel][label] = hit
+    return out
+
+
 def write_csv(path, sub):
     with open(path, "w", newline="") as f:
         w = csv.writer(f)
@@ -122,6 +138,8 @@ def main(argv=None):
     ap.add_argument("--scenarios", type=int, default=0, help="only the first N scenarios of the grid")
     ap.add_argument("--out", default="sweep_out")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--source", default="device", choices=["device", "reference"],
+                    help="device: Philox generator in HBM; reference: the reference's host generator + z-scoring")
     args = ap.parse_args(argv)
     os.makedirs(args.out, exist_ok=True)
     summary = []
@@ -129,13 +147,20 @@ def main(argv=None):
         if args.scenarios and i >= args.scenarios:
             break
         name = scenario_name(sc)
-        des = DeviceDesign.synthetic(args.n, args.d, np.float64 if args.dtype == "f64" else np.float32,
-                                     device=args.device, **sc)
+        dt = np.float64 if args.dtype == "f64" else np.float32
+        if args.source == "reference":
+            from . import datagen
+            A, b, _ = datagen.generate_correlated_design(args.n, args.d, **sc)
+            A, b = datagen.standardize(A, b)
+            des = DeviceDesign.from_host(A.astype(dt), b, device=args.device)
+        else:
+            des = DeviceDesign.synthetic(args.n, args.d, dt, device=args.device, **sc)
         traces, timing, meta = run_scenario(des, max_iter=args.max_iter)
         sub = suboptimality(traces)
         write_csv(os.path.join(args.out, f"benchmark_{name}.csv"), sub)
-        rec = {"scenario": name, "n": args.n, "d": args.d, **meta, "seconds": timing["total_s"],
-               "iters": {p: {k: len(v) for k, v in c.items()} for p, c in traces.items()}}
+        rec = {"scenario": name, "n": args.n, "d": args.d, "source": args.source, **meta, "seconds": timing["total_s"],
+               "iters": {p: {k: len(v) for k, v in c.items()} for p, c in traces.items()},
+               "iters_to_1e-5": first_below(sub)}
         summary.append(rec)
         print(json.dumps(rec), flush=True)
         des.close()
