@@ -205,7 +205,10 @@ def screened_path(system, alphas1, alpha2, step, chunk=8, tol=1e-8, max_iter=500
     iteration (iterative_solvers.py:199-221) on its restricted system.
 
     ``system`` provides subset(idx) / apply(X) / solve(...) / d (GramDesign; the CPU tests pass a numpy
-    stand-in).  rule_scale > 1 discards more than the rule allows (tests use it to force the KKT
+    stand-in).  The rule is evaluated once per chunk with the chunk's SMALLEST penalty, so it only
+    discards while 2 lam_min > lam_prev: a chunk must not span more than a factor 2 of the grid
+    (256 log-spaced penalties over three decades: chunk <= 25), otherwise every feature is kept
+    and the chunk costs what the unscreened path costs.  rule_scale > 1 discards more than the rule allows (tests use it to force the KKT
     repair loop).  Returns (X, info)."""
     alphas1 = np.ascontiguousarray(alphas1, dtype=np.float64).reshape(-1)
     d = system.d

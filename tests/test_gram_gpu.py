@@ -180,7 +180,10 @@ def test_screened_path_matches_unscreened_on_device():
     import oracle
     A, b = _design(4000, 512, 7)
     lam = float(np.max(np.abs(A.T @ b)))
-    alphas = lam * np.logspace(-0.02, -2.0, 40)
+    # 64 penalties over 1.5 decades, 8 per chunk: the smallest penalty of a chunk is 0.76 x the previous
+    # chunk's, so the rule's threshold 2 lam_min - lam_prev is positive (a chunk that spans more than a
+    # factor 2 keeps every feature: the rule has nothing to say there)
+    alphas = lam * np.logspace(-0.02, -1.5, 64)
     np.random.seed(0)
     L = oracle.estimate_lipschitz(A)
     des = DeviceDesign.from_host(A, b)

@@ -29,6 +29,10 @@ class _StandInDesign:
         self.shape = self.A.shape
         self.device = 0
         self.calls = {"grad": 0, "objective": 0}
+        self.closed = False
+
+    def close(self):
+        self.closed = True
 
     def grad(self, x, alpha2=0.0):
         self.calls["grad"] += 1
