@@ -83,6 +83,129 @@ extern "C" int fos_device_info(int device, int* sm_count, size_t* total_bytes, s
 // ------------------------------------------------------------------------------------------
 static inline int elem_size(int dtype) { return dtype == FOS_F64 ? 8 : 4; }
 
+
+// ------------------------------------------------------------------------------------------
+// recycling allocator (see fos_common.cuh)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock {
+    void* p;
+    size_t cap;
+    int device;  // -1: pinned host memory
+};
+std::mutex g_pool_mu;
+std::map<void*, PoolBlock> g_pool_live;   // blocks handed out
+std::vector<PoolBlock> g_pool_idle;       // blocks waiting for reuse (oldest first)
+constexpr size_t POOL_IDLE_DEVICE_MAX = 1536u << 20;  // per process, all devices
+constexpr size_t POOL_IDLE_PINNED_MAX = 96u << 20;
+
+bool pool_on() {
+    static const bool on = [] {
+        const char* e = getenv("FOS_POOL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+size_t pool_round(size_t bytes) {
+    if (bytes < 4096) return 4096;
+    if (bytes < (1u << 20)) return (bytes + 4095) & ~static_cast<size_t>(4095);
+    return (bytes + (1u << 20) - 1) & ~static_cast<size_t>((1u << 20) - 1);
+}
+void pool_release(const PoolBlock& b) {
+    if (b.device < 0) {
+        cudaFreeHost(b.p);
+    } else {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != b.device) cudaSetDevice(b.device);
+        cudaFree(b.p);
+        if (cur != b.device) cudaSetDevice(cur);
+    }
+}
+// evict idle blocks (oldest first) of one kind until at most `keep` bytes of it stay; lock held
+void pool_shrink(bool pinned, size_t keep) {
+    size_t total = 0;
+    for (const PoolBlock& b : g_pool_idle)
+        if ((b.device < 0) == pinned) total += b.cap;
+    for (size_t i = 0; i < g_pool_idle.size() && total > keep;) {
+        if ((g_pool_idle[i].device < 0) == pinned) {
+            total -= g_pool_idle[i].cap;
+            pool_release(g_pool_idle[i]);
+            g_pool_idle.erase(g_pool_idle.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
+cudaError_t pool_get(void** out, size_t bytes, bool pinned) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    int device = -1;
+    if (!pinned) {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return e;
+    }
+    const size_t want = pool_round(bytes);
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    // best fit among the idle blocks of this kind: never hand out more than twice the request
+    int best = -1;
+    for (size_t i = 0; i < g_pool_idle.size(); ++i) {
+        const PoolBlock& b = g_pool_idle[i];
+        if (b.device != device || b.cap < want || b.cap > 2 * want) continue;
+        if (best < 0 || b.cap < g_pool_idle[best].cap) best = static_cast<int>(i);
+    }
+    PoolBlock blk;
+    if (best >= 0) {
+        blk = g_pool_idle[best];
+        g_pool_idle.erase(g_pool_idle.begin() + best);
+    } else {
+        void* p = nullptr;
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaErrorMemoryAllocation) {  // make room: give the idle blocks back and try once more
+            cudaGetLastError();
+            pool_shrink(pinned, 0);
+            e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) return e;
+        blk = PoolBlock{p, want, device};
+    }
+    g_pool_live[blk.p] = blk;
+    *out = blk.p;
+    return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t fos_pool_malloc(void** p, size_t bytes) { return pool_get(p, bytes, false); }
+cudaError_t fos_pool_malloc_host(void** p, size_t bytes) { return pool_get(p, bytes, true); }
+
+void fos_pool_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pool_live.find(p);
+    if (it == g_pool_live.end()) {  // not ours (never happens for pool allocations): plain free
+        cudaFree(p);
+        cudaGetLastError();
+        return;
+    }
+    const PoolBlock blk = it->second;
+    g_pool_live.erase(it);
+    const bool pinned = blk.device < 0;
+    const size_t cap_kind = pinned ? POOL_IDLE_PINNED_MAX : POOL_IDLE_DEVICE_MAX;
+    if (!pool_on() || blk.cap > cap_kind) {
+        pool_release(blk);
+        return;
+    }
+    g_pool_idle.push_back(blk);
+    pool_shrink(pinned, cap_kind);
+}
+
+void fos_pool_trim() {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (const PoolBlock& b : g_pool_idle) pool_release(b);
+    g_pool_idle.clear();
+    cudaGetLastError();
+}
+
 static int design_common_init(fos_design* h, long long n, long long d, int dtype, int device) {
     FOS_REQUIRE(n >= 1 && d >= 1, "design must have at least one row and one column (got %lld x %lld)", n, d);
     FOS_REQUIRE(dtype == FOS_F64 || dtype == FOS_F32, "dtype must be FOS_F64 or FOS_F32");
@@ -136,7 +259,7 @@ static int design_alloc_work(fos_design* h) {
     const size_t o_row = o_g + up(vb);
     const size_t o_ctrl = o_row + up((h->n_parts + 1) * sizeof(long long));
     const size_t total = o_ctrl + up(sizeof(FosCtrl));
-    FOS_CUDA(cudaMalloc(&h->work_block, total));
+    FOS_CUDA(fos_pool_malloc(&h->work_block, total));
     FOS_CUDA(cudaMemsetAsync(h->work_block, 0, total, h->stream));
     char* wb = static_cast<char*>(h->work_block);
     h->partial_g = reinterpret_cast<double*>(wb + o_pg);
@@ -155,7 +278,7 @@ static int design_alloc_work(fos_design* h) {
     const size_t p_ctrl = 0;
     const size_t p_vec = p_ctrl + up(4 * sizeof(FosCtrl));
     const size_t p_scr = p_vec + up((2 * static_cast<size_t>(h->ldv) + 16) * sizeof(double));
-    FOS_CUDA(cudaMallocHost(&h->pin_block, p_scr + FOS_PIN_SCRATCH));
+    FOS_CUDA(fos_pool_malloc_host(&h->pin_block, p_scr + FOS_PIN_SCRATCH));
     char* pb = static_cast<char*>(h->pin_block);
     h->ctrl_host = reinterpret_cast<FosCtrl*>(pb + p_ctrl);
     h->vec_host = reinterpret_cast<double*>(pb + p_vec);
@@ -220,7 +343,7 @@ int fos_balance_rows(fos_design* h) {
     std::vector<int> slot(256 + P, 0);
     for (int i = 0; i < 256; ++i) slot[i] = i % P;
     for (int i = 0; i < P; ++i) slot[256 + i] = -1;  // 0xFFFFFFFF: never a pass number (31 bits)
-    if (h->sm_slot == nullptr) FOS_CUDA(cudaMalloc(&h->sm_slot, slot.size() * sizeof(int)));
+    if (h->sm_slot == nullptr) FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&h->sm_slot), slot.size() * sizeof(int)));
     FOS_CUDA(cudaMemcpy(h->sm_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice));
 
     std::lock_guard<std::mutex> lock(g_bal_mutex);
@@ -293,7 +416,7 @@ int fos_balance_rows(fos_design* h) {
     }
     if (it->second.empty()) {
         // equal blocks indexed by blockIdx (the default partition)
-        cudaFree(h->sm_slot);
+        fos_pool_free(h->sm_slot);
         h->sm_slot = nullptr;
         for (int c = 0; c <= P; ++c) h->row_lo_host[c] = (h->n * c) / P;
         FOS_CUDA(cudaMemcpy(h->row_lo, h->row_lo_host.data(), (P + 1) * sizeof(long long), cudaMemcpyHostToDevice));
@@ -310,15 +433,25 @@ static void blk_give(int device, void* p, size_t cap);  // matrix-block recyclin
 
 static void design_free(fos_design* h) {
     if (!h) return;
+    const bool dbg = getenv("FOS_UPLOAD_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto f0 = now();
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    const auto f1 = now();
     if (h->owns_A && h->A) blk_give(h->device, h->A, h->A_cap);
-    if (h->owns_b && h->b) cudaFree(h->b);
+    if (h->owns_b && h->b) fos_pool_free(h->b);
+    const auto f2 = now();
     fos_upload_gram_drop(h);
+    const auto f3 = now();
     void* bufs[] = {h->work_block, h->sm_slot, h->arena};
-    for (void* p : bufs)
-        if (p) cudaFree(p);
-    if (h->pin_block) cudaFreeHost(h->pin_block);
+    for (void* p : bufs) fos_pool_free(p);
+    const auto f4 = now();
+    fos_pool_free(h->pin_block);
+    if (dbg)
+        fprintf(stderr, "[fos] design_free: sync %.1f ms, A+b %.1f ms, gram %.1f ms, work/arena %.1f ms, pinned %.1f ms\n",
+                ms(f0, f1), ms(f1, f2), ms(f2, f3), ms(f3, f4), ms(f4, now()));
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -397,6 +530,7 @@ static void blk_give(int device, void* p, size_t cap) {
 }
 
 void fos_block_cache_trim() {
+    fos_pool_trim();
     std::lock_guard<std::mutex> lock(g_blk_mu);
     for (auto& kv : g_blk_cache) {
         cudaSetDevice(kv.first);
@@ -417,7 +551,7 @@ static int alloc_matrix(fos_design* h) {
         return FOS_ERR_NOMEM;
     }
     h->owns_A = true;
-    FOS_CUDA(cudaMalloc(&h->b, static_cast<size_t>(h->n) * sizeof(double)));
+    FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&h->b), static_cast<size_t>(h->n) * sizeof(double)));
     h->owns_b = true;
     return FOS_OK;
 }
@@ -1100,11 +1234,11 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
 
 int fos_arena_reserve(fos_design* h, size_t bytes, void** base) {
     if (bytes > h->arena_bytes) {
-        if (h->arena) cudaFree(h->arena);
+        fos_pool_free(h->arena);
         h->arena = nullptr;
         h->arena_bytes = 0;
         const size_t want = (bytes + (1u << 20) - 1) & ~static_cast<size_t>((1u << 20) - 1);
-        if (cudaMalloc(&h->arena, want) != cudaSuccess) {
+        if (fos_pool_malloc(&h->arena, want) != cudaSuccess) {
             cudaGetLastError();
             fos_set_error("cannot allocate %zu bytes of solver workspace on the device", want);
             return FOS_ERR_NOMEM;

@@ -219,6 +219,16 @@ struct fos_design {
 };
 
 constexpr size_t FOS_PIN_SCRATCH = 16384;
+// Recycling allocator for the per-design / per-call blocks (fos_api.cu).  cudaMalloc, cudaFree,
+// cudaMallocHost and cudaFreeHost are trips through the driver's global lock and sporadically take
+// 50-100 ms each on a busy host (measured around a 0.72 s upload: 'workspaces 94 ms', 'cudaFree(b)
+// 95 ms'); a drop-in caller creates and destroys a design per solver call, so freed blocks are kept
+// (per device, device and pinned memory apart, bounded) and handed to the next request of a similar
+// size.  fos_trim() releases them.
+cudaError_t fos_pool_malloc(void** p, size_t bytes);      // device memory of the current device
+cudaError_t fos_pool_malloc_host(void** p, size_t bytes); // pinned host memory
+void fos_pool_free(void* p);                              // either kind; nullptr is fine
+void fos_pool_trim();
 // Grow-only per-design device workspace: solver calls carve their per-call arrays out of it
 // instead of cudaMalloc/cudaFree pairs (milliseconds each once peer mappings exist).  The
 // previous contents are lost when it grows; one solver call at a time per design.

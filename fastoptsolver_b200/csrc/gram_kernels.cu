@@ -463,8 +463,8 @@ struct fos_gram {
 static void gram_free(fos_gram* g) {
     if (!g) return;
     cudaSetDevice(g->device);
-    if (g->G) cudaFree(g->G);
-    if (g->c) cudaFree(g->c);
+    fos_pool_free(g->G);
+    fos_pool_free(g->c);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -582,7 +582,7 @@ int fos_upload_gram_begin(fos_design* h, cudaStream_t s) {
     const auto b0 = std::chrono::steady_clock::now();
     h->up_W = static_cast<double*>(ws_take(h->device, wbytes));
     h->up_W_bytes = wbytes;
-    if (h->up_W == nullptr || cudaMalloc(&h->G_up, d * d * sizeof(double)) != cudaSuccess) {
+    if (h->up_W == nullptr || fos_pool_malloc(reinterpret_cast<void**>(&h->G_up), d * d * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         fos_upload_gram_drop(h);
         return FOS_OK;
@@ -639,7 +639,7 @@ int fos_upload_gram_finish(fos_design* h, cudaStream_t s) {
 
 void fos_upload_gram_drop(fos_design* h) {
     if (h->up_W) ws_give(h->device, h->up_W, h->up_W_bytes);
-    if (h->G_up) cudaFree(h->G_up);
+    fos_pool_free(h->G_up);
     h->up_W = nullptr;
     h->G_up = nullptr;
     h->G_state = 0;
@@ -748,8 +748,8 @@ extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
         FOS_CUDA(cudaEventCreate(&g->ev0));
         FOS_CUDA(cudaEventCreate(&g->ev1));
         const long long d = h->d;
-        FOS_CUDA(cudaMalloc(&g->G, static_cast<size_t>(d) * d * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&g->c, static_cast<size_t>(d) * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&g->G), static_cast<size_t>(d) * d * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&g->c), static_cast<size_t>(d) * sizeof(double)));
         // c = A^T b and b^T b from one pass of the streaming kernel with x = 0: g = -A^T b
         std::vector<double> zero(h->d, 0.0), gneg(h->d);
         double half_bb = 0.0;
@@ -872,9 +872,9 @@ extern "C" int fos_gram_subset(fos_gram* g, const int* idx, int n_idx, fos_gram*
         FOS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         FOS_CUDA(cudaEventCreate(&s->ev0));
         FOS_CUDA(cudaEventCreate(&s->ev1));
-        FOS_CUDA(cudaMalloc(&s->G, static_cast<size_t>(s->d) * s->d * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&s->c, static_cast<size_t>(s->d) * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&idx_dev, static_cast<size_t>(n_idx) * sizeof(int)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&s->G), static_cast<size_t>(s->d) * s->d * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&s->c), static_cast<size_t>(s->d) * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&idx_dev), static_cast<size_t>(n_idx) * sizeof(int)));
         FOS_CUDA(cudaMemcpyAsync(idx_dev, idx, static_cast<size_t>(n_idx) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
         FOS_CUDA(cudaStreamSynchronize(g->stream));  // the parent matrix is complete
         FOS_CUDA(cudaEventRecord(s->ev0, s->stream));
@@ -887,7 +887,7 @@ extern "C" int fos_gram_subset(fos_gram* g, const int* idx, int n_idx, fos_gram*
         return FOS_OK;
     };
     const int st = body();
-    if (idx_dev) cudaFree(idx_dev);
+    fos_pool_free(idx_dev);
     if (st != FOS_OK) {
         gram_free(s);
         return st;
@@ -902,7 +902,7 @@ extern "C" int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* 
     FOS_CUDA(cudaSetDevice(g->device));
     const size_t bytes = static_cast<size_t>(n_cols) * g->d * sizeof(double);
     double* buf = nullptr;
-    FOS_CUDA(cudaMalloc(&buf, 2 * bytes));
+    FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&buf), 2 * bytes));
     auto body = [&]() -> int {
         FOS_CUDA(cudaMemcpyAsync(buf, X, bytes, cudaMemcpyHostToDevice, g->stream));
         gram_apply_kernel<<<dim3(static_cast<unsigned>((g->d + 7) / 8), static_cast<unsigned>(n_cols)), dim3(256), 0,
@@ -913,7 +913,7 @@ extern "C" int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* 
         return FOS_OK;
     };
     const int st = body();
-    cudaFree(buf);
+    fos_pool_free(buf);
     return st;
 }
 
@@ -960,19 +960,19 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
     double* smax_host = nullptr;
     auto cleanup = [&]() {
         for (double* q : {Y0, Y1, X, a1, part, obj, spart, smax})
-            if (q) cudaFree(q);
-        if (smax_host) cudaFreeHost(smax_host);
+            fos_pool_free(q);
+        fos_pool_free(smax_host);
     };
     auto body = [&]() -> int {
-        FOS_CUDA(cudaMalloc(&Y0, mat * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&Y1, mat * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&X, mat * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&a1, Lpad * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&part, static_cast<size_t>(nblk) * Lpad * 4 * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&spart, static_cast<size_t>(nblk) * Lpad * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&obj, Lpad * sizeof(double)));
-        FOS_CUDA(cudaMalloc(&smax, sizeof(double)));
-        FOS_CUDA(cudaMallocHost(&smax_host, sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&Y0), mat * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&Y1), mat * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&X), mat * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&a1), Lpad * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&part), static_cast<size_t>(nblk) * Lpad * 4 * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&spart), static_cast<size_t>(nblk) * Lpad * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&obj), Lpad * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&smax), sizeof(double)));
+        FOS_CUDA(fos_pool_malloc_host(reinterpret_cast<void**>(&smax_host), sizeof(double)));
         FOS_CUDA(cudaMemsetAsync(Y0, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(Y1, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(X, 0, mat * sizeof(double), g->stream));
