@@ -142,7 +142,7 @@ extern "C" int fos_comm_window_alloc_fd(fos_design* h, int rank, int world, int*
     const CUmemAllocationProp prop = window_prop(h->device);
     size_t gran = 0;
     FOS_DRV(d.GetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
-    h->window_bytes = window_doubles(h) * sizeof(double) + (FOS_MAX_WORLD + 8) * sizeof(unsigned long long);
+    h->window_bytes = fos_window_bytes(h);
     h->vmm_size = (h->window_bytes + gran - 1) / gran * gran;
     h->vmm_gran = gran;
     CUmemGenericAllocationHandle handle = 0;
@@ -168,9 +168,7 @@ extern "C" int fos_comm_window_alloc_fd(fos_design* h, int rank, int world, int*
     FOS_CUDA(cudaMemset(h->window, 0, h->vmm_size));
     h->rank = rank;
     h->world = 1;  // becomes `world` once the peers are attached
-    h->peer.win[rank] = static_cast<double*>(h->window);
-    h->peer.flag[rank] = reinterpret_cast<unsigned long long*>(h->peer.win[rank] + window_doubles(h));
-    h->peer.epoch = h->peer.flag[rank] + FOS_MAX_WORLD;
+    fos_window_bind(h, rank, h->window);
     // the exchange counter starts at 1 so that a zeroed flag never satisfies a wait
     unsigned long long one = 1;
     FOS_CUDA(cudaMemcpy(h->peer.epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
@@ -199,8 +197,7 @@ extern "C" int fos_comm_attach_fd(fos_design* h, const int* fds, int world) {
         void* base = nullptr;
         if (map_local(d, handle, h->vmm_size, h->vmm_gran, h->device, &base) != FOS_OK) return FOS_ERR_COMM;
         h->vmm_ptr[r] = base;
-        h->peer.win[r] = static_cast<double*>(base);
-        h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
+        fos_window_bind(h, r, base);
     }
     h->world = world;
     return fos_comm_after_attach(h);

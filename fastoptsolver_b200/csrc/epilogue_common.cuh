@@ -194,12 +194,6 @@ __device__ __forceinline__ double2 reduced_column(const EpiArgs& e, int c, unsig
     return s;
 }
 
-__device__ __forceinline__ double prox_point(double y, double t, double g, double a1) {
-    double v = __dsub_rn(y, __dmul_rn(t, g));
-    if (a1 > 0.0) v = fos_soft_threshold(v, __dmul_rn(t, a1));
-    return v;
-}
-
 #define FOR_MY_COLUMN_PAIRS(c)                                                              \
     for (int c = 2 * (static_cast<int>(cg::this_cluster().block_rank()) * FOS_EPI_THREADS +  \
                       static_cast<int>(threadIdx.x));                                        \

@@ -13,6 +13,7 @@
 // Elementwise formulas use explicit round-to-nearest intrinsics (no FMA contraction) so that,
 // given the same gradient, they reproduce numpy's two-rounding arithmetic bit for bit.
 #include "epilogue_common.cuh"
+#include "pg_logic.cuh"
 
 namespace {
 
@@ -105,17 +106,10 @@ epilogue_kernel(const EpiArgs e) {
     }
 
     // ------------------------------------------------------------------ proximal-gradient engine
-    const int phase = C->phase;
-    if (phase == PH_DONE) return;
-    const int scheme = C->scheme, backtracking = C->backtracking, k = C->k;
-    const double a1 = C->alpha1, a2 = C->alpha2;
-    const double tau = C->tau, trial_t = C->trial_t;
-    const int obj_pending = C->obj_pending, want_obj = C->want_obj, obj_terms = C->obj_terms;
-    const int shrinks = C->shrinks, n_grad_calls = C->n_grad_calls;
-    const double gy_saved = C->gy, gd_saved = C->gd, cand_xx_saved = C->cand_xx;
-    const double pend_l2 = C->pend_l2, pend_l1 = C->pend_l1;
-    const double t_mom = C->t_mom, prev_step = C->prev_step;
-    const unsigned long long pass_t0 = C->pass_t0;
+    // (state machine and elementwise formulas: pg_logic.cuh, shared with the persistent solve kernel)
+    if (C->phase == PH_DONE) return;
+    const PgIn in = pg_read<false>(C);
+    const int phase = in.phase;
     const unsigned long long t_epi0 = fos_globaltimer();
 
     double s1, s2;
@@ -130,228 +124,29 @@ epilogue_kernel(const EpiArgs e) {
         reduced_scalars(e, sh, epoch, s1, s2);
     }
 
-    // Armijo test of the candidate evaluated by the pass that just ran (:191 / :306 / :101)
-    bool accept = false;
-    double t_new = trial_t;
-    if (phase == PH_TRIAL) {
-        double lhs = 0.5 * s2;
-        if (a2 > 0.0) lhs = __dadd_rn(lhs, __dmul_rn(0.5 * a2, cand_xx_saved));
-        const double rhs = __dadd_rn(gy_saved, __dmul_rn(C->armijo_c, gd_saved));
-        accept = lhs <= rhs;
-        if (!accept) t_new = __dmul_rn(trial_t, C->eta);
-    }
+    bool accept;
+    double t_new;
+    pg_armijo(in, s2, accept, t_new);
 
     // ---- elementwise 1: gradient, candidate point, local sums
-    enum { S_GG = 0, S_DX2 = 1, S_L1 = 2, S_XX = 3, S_GD = 4, S_YY = 5 };
     if (phase == PH_GRAD) {
-        FOR_MY_COLUMN_PAIRS(c) {
-            double2 g = reduced_column(e, c, epoch);
-            const double2 y = *reinterpret_cast<const double2*>(e.y + c);
-            const double2 xk = *reinterpret_cast<const double2*>(e.xk + c);
-            if (a2 > 0.0) {
-                g.x = __dadd_rn(g.x, __dmul_rn(a2, y.x));
-                g.y = __dadd_rn(g.y, __dmul_rn(a2, y.y));
-            }
-            *reinterpret_cast<double2*>(e.g + c) = g;
-            double2 cand;
-            cand.x = (c < e.d) ? prox_point(y.x, tau, g.x, a1) : 0.0;
-            cand.y = (c + 1 < e.d) ? prox_point(y.y, tau, g.y, a1) : 0.0;
-            *reinterpret_cast<double2*>(e.xc + c) = cand;
-            const double dx = cand.x - xk.x, dy = cand.y - xk.y;
-            sums[S_GG] = fma(g.y, g.y, fma(g.x, g.x, sums[S_GG]));
-            sums[S_DX2] = fma(dy, dy, fma(dx, dx, sums[S_DX2]));
-            sums[S_L1] += fabs(cand.x) + fabs(cand.y);
-            sums[S_XX] = fma(cand.y, cand.y, fma(cand.x, cand.x, sums[S_XX]));
-            sums[S_GD] = fma(g.y, cand.y - y.y, fma(g.x, cand.x - y.x, sums[S_GD]));
-            sums[S_YY] = fma(y.y, y.y, fma(y.x, y.x, sums[S_YY]));
-        }
+        FOR_MY_COLUMN_PAIRS(c) pg_elem1_grad<false>(e, in, c, reduced_column(e, c, epoch), sums);
     } else if (phase == PH_TRIAL) {
-        FOR_MY_COLUMN_PAIRS(c) {
-            const double2 xk = *reinterpret_cast<const double2*>(e.xk + c);
-            double2 cand;
-            if (accept) {
-                cand = *reinterpret_cast<const double2*>(e.xc + c);
-            } else {
-                const double2 g = *reinterpret_cast<const double2*>(e.g + c);
-                const double2 y = *reinterpret_cast<const double2*>(e.y + c);
-                cand.x = (c < e.d) ? prox_point(y.x, t_new, g.x, a1) : 0.0;
-                cand.y = (c + 1 < e.d) ? prox_point(y.y, t_new, g.y, a1) : 0.0;
-                *reinterpret_cast<double2*>(e.xc + c) = cand;
-                sums[S_GD] = fma(g.y, cand.y - y.y, fma(g.x, cand.x - y.x, sums[S_GD]));
-            }
-            const double dx = cand.x - xk.x, dy = cand.y - xk.y;
-            sums[S_DX2] = fma(dy, dy, fma(dx, dx, sums[S_DX2]));
-            sums[S_L1] += fabs(cand.x) + fabs(cand.y);
-            sums[S_XX] = fma(cand.y, cand.y, fma(cand.x, cand.x, sums[S_XX]));
-        }
+        FOR_MY_COLUMN_PAIRS(c) pg_elem1_trial<false>(e, in, c, accept, t_new, sums);
     }
     cluster_sum(sums, sh);
 
     // ---- scalar logic (identical in every thread)
-    int n_phase = phase, n_gmode = GM_SKIP, n_k = k, n_shrinks = shrinks;
-    int n_obj_pending = obj_pending, n_stop = C->stop_reason, n_ngrad = n_grad_calls;
-    double n_tau = tau, n_trial = trial_t, n_gy = gy_saved, n_gd = gd_saved, n_cxx = cand_xx_saved;
-    double n_pl2 = pend_l2, n_pl1 = pend_l1, n_tmom = t_mom, n_prev = prev_step;
-    bool do_update = false, obj_known = false;
-    double resolved_obj = 0.0;
-    bool resolve_obj = false;
-    bool ls_done = false;
+    const PgOut o = pg_decide(in, sums, s1, s2, accept, t_new);
 
-    if (phase == PH_GRAD) {
-        n_ngrad = n_grad_calls + 1;
-        if (obj_pending) {
-            resolved_obj = __dadd_rn(__dadd_rn(0.5 * s2, pend_l2), pend_l1);
-            resolve_obj = true;
-            n_obj_pending = 0;
-        }
-        if (scheme == FOS_SCHEME_NESTEROV && C->tol > 0.0 && sqrt(sums[S_GG]) < C->tol) {
-            n_stop = FOS_STOP_GRADNORM;
-            n_phase = PH_DONE;
-            n_gmode = GM_SKIP;
-        } else if (backtracking) {
-            n_trial = tau;
-            n_shrinks = 0;
-            n_gy = 0.5 * s1;
-            if (a2 > 0.0) n_gy = __dadd_rn(n_gy, __dmul_rn(0.5 * a2, sums[S_YY]));
-            n_gd = sums[S_GD];
-            n_cxx = sums[S_XX];
-            n_phase = PH_TRIAL;
-            n_gmode = GM_DOT2;
-        } else {
-            do_update = true;
-        }
-    } else if (phase == PH_TRIAL) {
-        if (accept) {
-            n_tau = trial_t;
-            ls_done = true;
-            do_update = true;
-            obj_known = true;
-        } else {
-            n_trial = t_new;
-            n_shrinks = shrinks + 1;
-            n_gd = sums[S_GD];
-            n_cxx = sums[S_XX];
-            n_gmode = GM_DOT2;
-        }
-    } else {  // PH_FINALOBJ
-        resolved_obj = __dadd_rn(__dadd_rn(0.5 * s2, pend_l2), pend_l1);
-        resolve_obj = true;
-        n_obj_pending = 0;
-        n_phase = PH_DONE;
-        n_gmode = GM_SKIP;
-    }
-
-    double beta = 0.0, this_step = 0.0;
-    bool plain_copy = false;
-    double new_obj = 0.0;
-    bool write_new_obj = false;
-    if (do_update) {
-        this_step = sqrt(sums[S_DX2]);
-        const double ratio = (prev_step > 0.0) ? this_step / prev_step : INFINITY;
-        if (scheme == FOS_SCHEME_NESTEROV) {
-            if (C->adaptive_restart && ratio > C->restart_thr) {
-                n_tmom = 1.0;
-                plain_copy = true;
-            } else {
-                n_tmom = 0.5 * (1.0 + sqrt(1.0 + 4.0 * (t_mom * t_mom)));
-                beta = (t_mom - 1.0) / n_tmom;
-            }
-        } else if (scheme == FOS_SCHEME_DELTA) {
-            const double kk = static_cast<double>(k + 1);
-            beta = kk / ((kk + 1.0) + C->delta);
-        } else {
-            plain_copy = true;
-        }
-        if (want_obj) {
-            const double l2t = (obj_terms & 2) ? __dmul_rn(0.5 * a2, sums[S_XX]) : 0.0;
-            const double l1t = (obj_terms & 1) ? __dmul_rn(a1, sums[S_L1]) : 0.0;
-            if (obj_known) {
-                new_obj = __dadd_rn(__dadd_rn(0.5 * s2, l2t), l1t);
-                write_new_obj = true;
-            } else {
-                n_pl2 = l2t;
-                n_pl1 = l1t;
-                n_obj_pending = 1;
-            }
-        }
-        n_k = k + 1;
-        n_prev = this_step;
-        bool stop = false;
-        if (C->tol > 0.0 && this_step < C->tol) {
-            stop = true;
-            n_stop = FOS_STOP_STEP;
-        } else if (scheme != FOS_SCHEME_ISTA && C->tol_ratio > 0.0 && ratio < C->tol_ratio) {
-            stop = true;
-            n_stop = FOS_STOP_RATIO;
-        } else if (n_k >= C->max_iter) {
-            stop = true;
-            n_stop = FOS_STOP_MAXITER;
-        }
-        if (stop) {
-            n_phase = n_obj_pending ? PH_FINALOBJ : PH_DONE;
-            n_gmode = n_obj_pending ? GM_DOT2 : GM_SKIP;
-        } else {
-            n_phase = PH_GRAD;
-            n_gmode = GM_GRAD | (n_obj_pending ? GM_DOT2 : 0);
-        }
-
-        // ---- elementwise 2: momentum point, roll the iterate, history row
-        double* hrow = (e.hist.x_hist != nullptr) ? e.hist.x_hist + static_cast<size_t>(k + 1) * e.d : nullptr;
-        FOR_MY_COLUMN_PAIRS(c) {
-            const double2 cand = *reinterpret_cast<const double2*>(e.xc + c);
-            const double2 xk = *reinterpret_cast<const double2*>(e.xk + c);
-            double2 yn;
-            if (plain_copy) {
-                yn = cand;
-            } else {
-                yn.x = __dadd_rn(cand.x, __dmul_rn(beta, __dsub_rn(cand.x, xk.x)));
-                yn.y = __dadd_rn(cand.y, __dmul_rn(beta, __dsub_rn(cand.y, xk.y)));
-            }
-            *reinterpret_cast<double2*>(e.y + c) = yn;
-            *reinterpret_cast<double2*>(e.xk + c) = cand;
-            if (hrow != nullptr) {
-                if (c < e.d) hrow[c] = cand.x;
-                if (c + 1 < e.d) hrow[c + 1] = cand.y;
-            }
-        }
+    // ---- elementwise 2: momentum point, roll the iterate, history row
+    if (o.do_update) {
+        FOR_MY_COLUMN_PAIRS(c) pg_elem2<false>(e, in, o, c);
     }
 
     if (leader) {
-        const float dt_ms = static_cast<float>(static_cast<double>(fos_globaltimer() - pass_t0) * 1e-6);
-        if (phase == PH_GRAD && e.hist.grad_ms) e.hist.grad_ms[n_grad_calls] = dt_ms;
-        if (phase == PH_TRIAL && e.hist.ls_ms) e.hist.ls_ms[k] += dt_ms;
-        if (resolve_obj && e.hist.obj_hist && k >= 1) e.hist.obj_hist[k - 1] = resolved_obj;
-        if (write_new_obj && e.hist.obj_hist) e.hist.obj_hist[k] = new_obj;
-        if (ls_done && e.hist.ls_iters) e.hist.ls_iters[k] = shrinks;
-        if (do_update) {
-            if (e.hist.t_hist) e.hist.t_hist[k + 1] = n_tau;
-            if (e.hist.step_hist) e.hist.step_hist[k] = this_step;
-        }
-        C->epi_ns += fos_globaltimer() - t_epi0;
-        C->xchg_ns += t_x1 - t_x0;
         if (e.world > 1) *e.peer.epoch = epoch + 1;
-        if (!comm_ok) {  // a peer never arrived: abort the solve, the host reports FOS_ERR_COMM
-            n_phase = PH_DONE;
-            n_gmode = GM_SKIP;
-            n_stop = -1;
-        }
-        C->phase = n_phase;
-        C->g_mode = n_gmode;
-        C->k = n_k;
-        C->shrinks = n_shrinks;
-        C->obj_pending = n_obj_pending;
-        C->stop_reason = n_stop;
-        C->n_grad_calls = n_ngrad;
-        C->n_passes += 1;
-        C->tau = n_tau;
-        C->trial_t = n_trial;
-        C->gy = n_gy;
-        C->gd = n_gd;
-        C->cand_xx = n_cxx;
-        C->pend_l2 = n_pl2;
-        C->pend_l1 = n_pl1;
-        C->t_mom = n_tmom;
-        C->prev_step = n_prev;
+        pg_commit(C, e.hist, in, o, comm_ok, t_epi0, t_x1 - t_x0);
     }
 }
 

@@ -44,6 +44,11 @@ cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cu
         attrs[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
     }
+    if (cluster_x < 0) {  // cooperative launch (grid-wide barriers inside the kernel)
+        attrs[n].id = cudaLaunchAttributeCooperative;
+        attrs[n].val.cooperative = 1;
+        ++n;
+    }
     if (cluster_x > 0) {
         attrs[n].id = cudaLaunchAttributeClusterDimension;
         attrs[n].val.clusterDim.x = cluster_x;
@@ -220,15 +225,29 @@ static int design_common_init(fos_design* h, long long n, long long d, int dtype
     }
     FOS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
     FOS_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    FOS_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        fos_set_error("device %d is sm_%d%d; libfos_b200 contains sm_100a code only", device, prop.major,
-                      prop.minor);
+    // two attribute queries, cached per device: cudaGetDeviceProperties fills ~100 fields (some through
+    // the driver's global lock) and took 12-128 ms per design on a busy host
+    static std::mutex prop_mu;
+    static std::map<int, std::pair<int, int>> prop_cache;  // device -> (cc major * 10 + minor, SM count)
+    std::pair<int, int> pr;
+    {
+        std::lock_guard<std::mutex> lock(prop_mu);
+        auto it = prop_cache.find(device);
+        if (it == prop_cache.end()) {
+            int major = 0, minor = 0, sms = 0;
+            FOS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+            FOS_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+            FOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            it = prop_cache.emplace(device, std::make_pair(major * 10 + minor, sms)).first;
+        }
+        pr = it->second;
+    }
+    if (pr.first / 10 != 10) {
+        fos_set_error("device %d is sm_%d; libfos_b200 contains sm_100a code only", device, pr.first);
         return FOS_ERR_UNSUPPORTED;
     }
     h->device = device;
-    h->sm_count = prop.multiProcessorCount;
+    h->sm_count = pr.second;
     h->n = n;
     h->d = static_cast<int>(d);
     h->dtype = dtype;
@@ -258,7 +277,8 @@ static int design_alloc_work(fos_design* h) {
     const size_t o_xc = o_y + up(vb), o_xk = o_xc + up(vb), o_g = o_xk + up(vb);
     const size_t o_row = o_g + up(vb);
     const size_t o_ctrl = o_row + up((h->n_parts + 1) * sizeof(long long));
-    const size_t total = o_ctrl + up(sizeof(FosCtrl));
+    const size_t o_sync = o_ctrl + up(sizeof(FosCtrl));
+    const size_t total = o_sync + (h->kern_kind == 1 ? up(sizeof(FosGridSync)) : 0);
     FOS_CUDA(fos_pool_malloc(&h->work_block, total));
     FOS_CUDA(cudaMemsetAsync(h->work_block, 0, total, h->stream));
     char* wb = static_cast<char*>(h->work_block);
@@ -270,6 +290,7 @@ static int design_alloc_work(fos_design* h) {
     h->g = reinterpret_cast<double*>(wb + o_g);
     h->row_lo = reinterpret_cast<long long*>(wb + o_row);
     h->ctrl = reinterpret_cast<FosCtrl*>(wb + o_ctrl);
+    h->gsync = (h->kern_kind == 1) ? reinterpret_cast<FosGridSync*>(wb + o_sync) : nullptr;  // zeroed with the block
     // row partition of the streaming kernel: equal blocks to start with
     h->row_lo_host.resize(h->n_parts + 1);
     for (int c = 0; c <= h->n_parts; ++c) h->row_lo_host[c] = (h->n * c) / h->n_parts;
@@ -1065,6 +1086,17 @@ extern "C" int fos_debug_cta_times(fos_design* h, int mode, long long* out, int 
     return FOS_OK;
 }
 
+extern "C" int fos_debug_solve_profile(fos_design* h, unsigned long long* out9, int reset) {
+    FOS_REQUIRE(h && out9, "null pointer argument");
+    for (int i = 0; i < 9; ++i) out9[i] = 0;
+    if (h->gsync == nullptr) return FOS_OK;
+    FOS_CUDA(cudaSetDevice(h->device));
+    FOS_CUDA(cudaStreamSynchronize(h->stream));
+    FOS_CUDA(cudaMemcpy(out9, h->gsync->prof, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) FOS_CUDA(cudaMemset(h->gsync->prof, 0, sizeof(h->gsync->prof)));
+    return FOS_OK;
+}
+
 extern "C" int fos_design_lambda_max(fos_design* h, double* out) {
     FOS_REQUIRE(h && out, "null pointer argument");
     std::vector<double> zero(h->d, 0.0), g(h->d);
@@ -1224,6 +1256,7 @@ extern "C" int fos_power_iter(fos_design* h, const double* v0, int n_iter, doubl
     FOS_CUDA(cudaStreamSynchronize(h->stream));
     if (c->stop_reason < 0) {
         fos_set_error("multi-GPU exchange timed out: a peer rank never arrived");
+        h->fused_ok = false;  // the grid counters of an abandoned launch are not reusable
         return FOS_ERR_COMM;
     }
     *L_out = c->L;
@@ -1357,9 +1390,24 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     FOS_CUDA(cudaEventRecord(h->ev0, h->stream));
     const auto t_host1 = std::chrono::steady_clock::now();
     long long pairs = 0;
-    if (K > 0)
+    bool fused = K > 0 && fos_solve_stages(h) > 0;
+    if (fused) {
+        // ONE launch of the persistent kernel runs every pass, the in-kernel epilogues and (row-sharded
+        // designs) the peer exchange; it leaves when the state machine reaches PH_DONE.  A refused
+        // launch (the cooperative launch cannot place every CTA: SMs reserved by another context)
+        // switches the design to the two-launch path for good.
+        if (fos_launch_solve(h, hist, max_pairs) == FOS_OK) {
+            pairs = 1;
+        } else {
+            cudaGetLastError();
+            h->fused_ok = false;
+            fused = false;
+        }
+    }
+    if (!fused && K > 0) {
         FOS_TRY(drive_passes(h, EOP_PG, hist, max_pairs, [](const FosCtrl& s) { return s.phase == PH_DONE; }, &pairs,
                              exact));
+    }
     FOS_CUDA(cudaEventRecord(h->ev1, h->stream));
     const auto t_host2 = std::chrono::steady_clock::now();
 
@@ -1369,6 +1417,7 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     FOS_CUDA(cudaStreamSynchronize(h->stream));
     if (c->stop_reason < 0) {
         fos_set_error("multi-GPU exchange timed out: a peer rank never arrived");
+        h->fused_ok = false;  // the grid counters of an abandoned launch are not reusable
         return FOS_ERR_COMM;
     }
     if (c->phase != PH_DONE && K > 0) {
@@ -1396,6 +1445,12 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     r->exchange_ms = static_cast<float>(c->xchg_ns * 1e-6);
     r->grad_kernel_ms = 0.f;
     r->grad_kernel_launches = 0;
+    if (fused) {
+        // device-stamped (%globaltimer) duration of the gradient phases: pass start -> every CTA's partials
+        // published; the rest of loop_ms is the in-kernel tails
+        r->grad_kernel_ms = static_cast<float>(c->grad_ns * 1e-6);
+        r->grad_kernel_launches = c->n_passes;
+    }
     // passes launched after the device reported completion exit immediately: count only the
     // ones that did work (the first n_passes)
     for (size_t i = 0; i + 1 < h->prof_used && static_cast<int>(i / 2) < c->n_passes; i += 2) {
@@ -1452,7 +1507,24 @@ extern "C" int fos_prox_elastic_net(const double* v, int64_t len, double tau, do
 // multi-GPU plumbing: peer-memory exchange windows (CUDA IPC), used by the fused all-reduce
 // inside the epilogue kernel
 // ------------------------------------------------------------------------------------------
+// Layout: [pull region: 2 slots x (ldv + PAD) doubles][FOS_MAX_WORLD + 8 u64: arrival flags, exchange counter]
+//         [push region: 2 slots x FOS_MAX_WORLD x (ldv + PAD) doubles][FOS_MAX_WORLD x FOS_MAX_PARTS u64 flags]
 static size_t window_doubles(const fos_design* h) { return 2 * static_cast<size_t>(h->ldv + FOS_WIN_PAD); }
+static size_t window_push_doubles(const fos_design* h) {
+    return 2 * static_cast<size_t>(FOS_MAX_WORLD) * static_cast<size_t>(h->ldv + FOS_WIN_PAD);
+}
+size_t fos_window_bytes(const fos_design* h) {
+    return window_doubles(h) * sizeof(double) + (FOS_MAX_WORLD + 8) * sizeof(unsigned long long) +
+           window_push_doubles(h) * sizeof(double) +
+           static_cast<size_t>(FOS_MAX_WORLD) * FOS_MAX_PARTS * sizeof(unsigned long long);
+}
+void fos_window_bind(fos_design* h, int r, void* base) {
+    h->peer.win[r] = static_cast<double*>(base);
+    h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
+    h->peer.fwin[r] = reinterpret_cast<double*>(h->peer.flag[r] + FOS_MAX_WORLD + 8);
+    h->peer.fflag[r] = reinterpret_cast<unsigned long long*>(h->peer.fwin[r] + window_push_doubles(h));
+    if (r == h->rank) h->peer.epoch = h->peer.flag[r] + FOS_MAX_WORLD;
+}
 
 extern "C" int fos_comm_window_alloc(fos_design* h, int rank, int world, void* ipc_handle_out64) {
     FOS_REQUIRE(h && ipc_handle_out64, "null pointer argument");
@@ -1461,7 +1533,7 @@ extern "C" int fos_comm_window_alloc(fos_design* h, int rank, int world, void* i
     FOS_REQUIRE(h->window == nullptr, "exchange window already allocated");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     FOS_CUDA(cudaSetDevice(h->device));
-    h->window_bytes = window_doubles(h) * sizeof(double) + (FOS_MAX_WORLD + 8) * sizeof(unsigned long long);
+    h->window_bytes = fos_window_bytes(h);
     FOS_CUDA(cudaMalloc(&h->window, h->window_bytes));
     FOS_CUDA(cudaMemset(h->window, 0, h->window_bytes));
     cudaIpcMemHandle_t hd;
@@ -1470,9 +1542,7 @@ extern "C" int fos_comm_window_alloc(fos_design* h, int rank, int world, void* i
     h->rank = rank;
     h->world = 1;  // becomes `world` once the peers are attached
     h->peer_base[rank] = nullptr;
-    h->peer.win[rank] = static_cast<double*>(h->window);
-    h->peer.flag[rank] = reinterpret_cast<unsigned long long*>(h->peer.win[rank] + window_doubles(h));
-    h->peer.epoch = h->peer.flag[rank] + FOS_MAX_WORLD;
+    fos_window_bind(h, rank, h->window);
     // the exchange counter starts at 1 so that a zeroed flag never satisfies a wait
     unsigned long long one = 1;
     FOS_CUDA(cudaMemcpy(h->peer.epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
@@ -1495,8 +1565,7 @@ extern "C" int fos_comm_attach(fos_design* h, const void* ipc_handles, int world
             return FOS_ERR_COMM;
         }
         h->peer_base[r] = base;
-        h->peer.win[r] = static_cast<double*>(base);
-        h->peer.flag[r] = reinterpret_cast<unsigned long long*>(h->peer.win[r] + window_doubles(h));
+        fos_window_bind(h, r, base);
     }
     h->world = world;
     return fos_comm_after_attach(h);

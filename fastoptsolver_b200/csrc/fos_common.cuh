@@ -84,6 +84,8 @@ struct FosCtrl {
     double tau, t_mom, prev_step, trial_t, gy, gd, cand_xx, pend_l2, pend_l1;
     unsigned long long pass_t0;  // %globaltimer at the start of the current pass
     unsigned long long epi_ns, xchg_ns;  // accumulated epilogue time / time spent waiting for peers
+    unsigned long long grad_ns;          // persistent solve kernel: accumulated time from the start of a pass until
+                                         // every CTA has published its partials (the gradient phase proper)
     // ---- power iteration
     double L, L_prev, ptol;
     int pit, pit_max;
@@ -109,9 +111,30 @@ struct FosPeer {
     double* win[8];                // win[r] = rank r's window as mapped in this process
     unsigned long long* flag[8];   // flag[r] = rank r's arrival counters, one per source rank
     unsigned long long* epoch;     // device-resident exchange counter (identical on all ranks)
+    // second region of the same window, used by the persistent solve kernel (push model): every rank
+    // WRITES its column slices into all windows, [2 slots][FOS_MAX_WORLD source ranks][ldv + FOS_WIN_PAD],
+    // and signals per (source rank, CTA): fflag[r][src * FOS_MAX_PARTS + cta] in rank r's window
+    double* fwin[8];
+    unsigned long long* fflag[8];
 };
 constexpr int FOS_WIN_PAD = 8;     // doubles after the ldv payload: [s1, s2, spare...]
 constexpr int FOS_MAX_WORLD = 8;
+constexpr int FOS_MAX_PARTS = 160; // >= CTAs of the streaming kernel (one per SM)
+
+// Grid-wide synchronisation state of the persistent solve kernel (device memory, zeroed once when the
+// design is created, never reset: all counters are monotonic).
+struct FosGridSync {
+    unsigned long long arrive0, pad0[15];  // one 128-byte line per counter
+    unsigned long long arrive1, pad1[15];
+    unsigned long long arrive2, pad2[15];
+    unsigned long long gen, pad3[15];      // passes completed (written by the leader before the last barrier of a pass)
+    int abort, pad4[31];                   // set when a wait timed out: every CTA leaves
+    double scal[FOS_MAX_PARTS][FOS_NSCAL]; // per-CTA column-slice sums of the current pass
+    // phase profile of CTA 0 (ns, accumulated over passes): [0] streaming loop, [1] wait at barrier 1,
+    // [2] slice sums, [3] peer exchange, [4] elementwise 1 + slice scalars, [5] barrier 2, [6] scalar totals +
+    // decision + elementwise 2 + commit, [7] barrier 3, [8] passes
+    unsigned long long prof[16];
+};
 
 // Everything the gradient kernel needs.
 struct GradArgs {
@@ -193,6 +216,8 @@ struct fos_design {
     FosPeer peer{};
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
+    FosGridSync* gsync = nullptr;  // persistent solve kernel (streaming designs only)
+    bool fused_ok = false;         // the whole solve may run as ONE launch of the persistent kernel
     bool lite_ok = false;         // a gradient-only kernel variant exists for this shape
     bool grad_only_hint = false;  // the running loop never asks for the second dot
     unsigned long long* cta_times = nullptr;  // debug buffer (fos_debug_cta_times)
@@ -238,6 +263,12 @@ int fos_arena_reserve(fos_design* h, size_t bytes, void** base);
 cudaError_t fos_launch_ex(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args,
                           bool pdl, int cluster_x);
 int fos_launch_grad(fos_design* h, int mode_override);
+// persistent solve kernel: runs passes (gradient + in-kernel epilogue + peer exchange) until the state
+// machine reports PH_DONE or max_passes have run.  FOS_ERR_UNSUPPORTED when the design does not qualify.
+int fos_launch_solve(fos_design* h, const FosHist& hist, long long max_passes);
+int fos_solve_stages(const fos_design* h);  // ring depth the persistent kernel would use; 0 = not eligible
+size_t fos_window_bytes(const fos_design* h);              // exchange window: both regions + flags
+void fos_window_bind(fos_design* h, int r, void* base);    // point peer.{win,flag,fwin,fflag}[r] into a mapped window
 int fos_launch_epilogue(fos_design* h, int op, int g_mode_ran, const FosHist& hist, double a1,
                         double a2, int bits);
 int fos_grad_plan(fos_design* h);

@@ -17,6 +17,7 @@
 //
 // HBM bound: algorithmic bytes per pass = n*lda*sizeof(T) + 8n; 4 flop / 8 B in fp64.
 #include "fos_common.cuh"
+#include "pg_logic.cuh"
 
 namespace {
 
@@ -114,10 +115,16 @@ struct StreamSmem {
 // Consumer loop, specialised on the pass mode.  GRAD: first dot + rank-1 update;
 // DOT2: second dot.  Column guards are folded into per-thread shared-memory offsets
 // (an out-of-range column reads offset 0 and multiplies it by a zero vector entry).
-template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2>
+// WRAP (persistent solve kernel): the ring keeps running across passes -- once the last stages of this
+// pass have been requested, freed slots are refilled with the FIRST stages of the next pass over the
+// same rows (A never changes), so HBM keeps streaming while the pass's tail runs; slot_io / parity_io
+// carry the ring position from pass to pass, and the vectors are read through L2 (other CTAs of the
+// same launch wrote them).  Requires nst >= nstage.
+template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2, bool WRAP = false>
 __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
                                                unsigned char* ring, int stage_bytes, int nstage,
-                                               long long lo, long long hi, bool use_b, uint64_t pol, int cta) {
+                                               long long lo, long long hi, bool use_b, uint64_t pol, int cta,
+                                               int& slot_io, uint32_t& parity_io) {
     constexpr int VEC = Vec<T>::N;
     constexpr int NV = CPT / VEC;
     constexpr int NW = NT / 32;
@@ -134,8 +141,8 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const int c = c0 + e;
-            v1[j][e] = (GRAD && c < a.d) ? a.v1[c] : 0.0;
-            v2[j][e] = (DOT2 && c < a.d) ? a.v2[c] : 0.0;
+            v1[j][e] = (GRAD && c < a.d) ? (WRAP ? __ldcg(a.v1 + c) : a.v1[c]) : 0.0;
+            v2[j][e] = (DOT2 && c < a.d) ? (WRAP ? __ldcg(a.v2 + c) : a.v2[c]) : 0.0;
             acc[j][e] = 0.0;
         }
     }
@@ -152,8 +159,8 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     if (b_lane && b_left > R) b_nxt = __ldg(bp + R);
 
     const uint32_t ring_u32 = smem_u32(ring);
-    int slot = 0;
-    uint32_t parity = 0;
+    int slot = slot_io;
+    uint32_t parity = parity_io;
     for (int s = 0; s < nst; ++s) {
         double b_far = 0.0;
         if (b_lane && b_left > 2 * R) b_far = __ldg(bp + 2 * R);
@@ -246,8 +253,9 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         __syncthreads();
         // Every consumer has copied stage s into registers before arriving at the barrier, so
         // its slot is free: thread 0 refills it with stage s + nstage (no empty barriers needed).
-        if (tid == 0 && s + nstage < nst) {
-            const long long rs = lo + static_cast<long long>(s + nstage) * R;
+        if (tid == 0 && (WRAP || s + nstage < nst)) {
+            const int ns = (s + nstage < nst) ? s + nstage : s + nstage - nst;  // >= nst: stage of the next pass
+            const long long rs = lo + static_cast<long long>(ns) * R;
             const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
             const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
             mbar_expect_tx(&sm.full_bar[slot], bytes);
@@ -301,6 +309,8 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         }
     }
 
+    slot_io = slot;
+    parity_io = parity;
     if (GRAD) {
         double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
 #pragma unroll
@@ -698,11 +708,13 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         return;
     }
     const bool use_b = !(mode & GM_NOB);
+    int slot0 = 0;
+    uint32_t par0 = 0;
     if (LITE) {
         if constexpr (SKEW)
             stream_consume_skew<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
         else
-            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
+            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
         return;
     }
     switch (mode & (GM_GRAD | GM_DOT2)) {
@@ -710,20 +722,473 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
             if constexpr (SKEW)
                 stream_consume_skew<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             else
-                stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
+                stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
         case GM_DOT2:
             if constexpr (SKEW)
                 stream_consume_skew<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             else
-                stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
+                stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
         default:
             if constexpr (SKEW)
                 stream_consume_skew<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
             else
-                stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
+                stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Persistent solve kernel: ONE launch runs a whole proximal-gradient solve (fista / fista_delta /
+// ista of the reference, iterative_solvers.py:65-344).  Every pass is the streaming loop above
+// followed, in the same kernel, by what used to be a second launch (epilogue_kernel):
+//
+//   1. every CTA publishes its partial A^T r (and residual norms)            -> grid barrier 1
+//   2. the d columns are sliced over ALL CTAs (14 column pairs each at d = 4096): a CTA sums its
+//      slice over the P partials (two-level fixed order: groups of 8, then the groups)
+//   3. row-sharded designs: the slice is PUSHED into every rank's window over NVLink, followed by one
+//      release-flag per (rank, CTA); a CTA waits only for ITS slice from the peers and sums the
+//      ranks in rank order (bit-identical on every rank) -- the all-reduce of the d-vector is done
+//      by 148 independent slice exchanges that overlap each other
+//   4. soft threshold / Armijo candidate for the slice (pg_logic.cuh), slice sums  -> grid barrier 2
+//   5. every CTA forms the same scalars, takes the same decision, applies the momentum step to its
+//      slice; CTA 0 writes the control block and the history scalars          -> grid barrier 3
+//
+// While 1-5 run, the bulk-copy ring is already refilling with the first stages of the next pass
+// (WRAP in stream_consume), so HBM idles for a few microseconds per pass instead of a launch
+// boundary + an epilogue launch.  The host launches once and synchronises once.
+//
+// All cross-CTA data is read through L2 (ld.global.cg / volatile) -- the L1 of an SM may hold the
+// previous pass's lines.  The grid barriers are monotonic counters (never reset); every wait has a
+// deadline and an abort flag so that a lost peer or a non-resident CTA ends the launch with an
+// error instead of hanging the device.  Requires all CTAs co-resident: grid = one CTA per SM,
+// launched cooperatively.
+// ------------------------------------------------------------------------------------------
+constexpr int TAIL_GS = 8;                                   // partials summed per group
+constexpr int TAIL_NG = (FOS_MAX_PARTS + TAIL_GS - 1) / TAIL_GS;
+constexpr int TAIL_PW = 28;                                  // most column pairs per CTA slice (ldv 8192 / 148 CTAs)
+
+struct TailSmem {
+    double2 gsum[TAIL_NG][TAIL_PW];   // group sums of the slice
+    double2 ssum[TAIL_NG];            // group sums of the residual-norm pair
+    double red[FOS_NSCAL][TAIL_PW];   // per-thread slice sums -> CTA sums
+    double grp[TAIL_NG][FOS_NSCAL];   // group sums of the per-CTA scalars
+    double tot[FOS_NSCAL];
+    double s12[2];
+    int ok;
+    // CTA 0 only: running totals of the timing fields of the control block (stored, never re-read from HBM)
+    unsigned long long acc_epi, acc_xchg, acc_grad;
+    int acc_passes;
+    // copy of the control block taken at the top of a pass by one coalesced warp read: 148 CTAs x ~30
+    // scalar reads of the same three lines after barrier 1 were a measurable L2 hot spot (3 us)
+    __align__(16) FosCtrl ctrl;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld_relaxed_sys_v2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v2(double* p, double2 v) {
+    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+constexpr unsigned long long GRID_WAIT_NS = 20ull * 1000000000ull;   // a CTA of this grid never arrived
+constexpr unsigned long long PEER_WAIT_NS = 60ull * 1000000000ull;   // a peer rank never arrived
+
+// Arrive on a monotonic grid counter and wait until `target` arrivals.  Returns false when the launch
+// is being abandoned (deadline passed here, or another CTA raised the abort flag).
+__device__ __forceinline__ bool grid_barrier(unsigned long long* ctr, unsigned long long target, FosGridSync* gs,
+                                             TailSmem& ts) {
+    __syncthreads();  // every thread's writes of this phase are ordered before thread 0's release
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_gpu_add(ctr, 1ull);
+        bool ok = true;
+        if (ld_acquire_gpu_u64(ctr) < target) {
+            const unsigned long long t0 = fos_globaltimer();
+            unsigned spins = 0;
+            while (ld_acquire_gpu_u64(ctr) < target) {
+                if ((++spins & 1023u) == 0u) {
+                    if (*reinterpret_cast<volatile int*>(&gs->abort) != 0 || fos_globaltimer() - t0 > GRID_WAIT_NS) {
+                        atomicExch(&gs->abort, 1);
+                        ok = false;
+                        break;
+                    }
+                }
+            }
+        }
+        __threadfence();
+        ts.ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    return ts.ok != 0;
+}
+
+// two-level fixed-order sum of P values per thread-item: groups of TAIL_GS consecutive partials, then
+// the groups in order (deterministic whatever CTA runs it)
+template <typename T, int NT, int CPT, int R, bool LITE>
+__global__ void __launch_bounds__(NT, 1)
+solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stage_bytes, int nstage, long long max_passes) {
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(16) StreamSmem<NW, R> sm;
+    __shared__ __align__(16) TailSmem ts;
+    __shared__ int s_cta;
+
+    const int tid = threadIdx.x;
+    const int P = gridDim.x;
+    uint64_t pol = 0;
+    if (tid == 0) {
+        int cta0 = blockIdx.x;
+        if (a.sm_slot != nullptr) {  // SM-indexed partition: claimed once, kept for every pass of the launch
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int s = a.sm_slot[smid & 255u];
+            for (int k = 0; k < P; ++k, s = (s + 1 == P) ? 0 : s + 1)
+                if (atomicExch(&a.slot_claim[s], a.pass_no) != a.pass_no) break;
+            cta0 = s;
+        }
+        s_cta = cta0;
+        const long long lo0 = a.row_lo[cta0], hi0 = a.row_lo[cta0 + 1];
+        const int nst0 = static_cast<int>((hi0 - lo0 + R - 1) / R);
+        for (int s = 0; s < nstage; ++s) mbar_init(&sm.full_bar[s], 1);
+        mbar_init(&sm.red_bar[0], NW * R * 2);
+        mbar_init(&sm.red_bar[1], NW * R * 2);
+        mbar_fence_init();
+        pol = l2_evict_first_policy();
+        const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
+        for (int s = 0; s < nstage && s < nst0; ++s) {  // the host guarantees nst0 >= nstage
+            const long long rs = lo0 + static_cast<long long>(s) * R;
+            const int nr = static_cast<int>(min(static_cast<long long>(R), hi0 - rs));
+            const uint32_t bytes = static_cast<uint32_t>(nr * row_bytes);
+            mbar_expect_tx(&sm.full_bar[s], bytes);
+            bulk_g2s(ring + static_cast<size_t>(s) * stage_bytes,
+                     static_cast<const unsigned char*>(a.A) + static_cast<size_t>(rs) * row_bytes, bytes,
+                     &sm.full_bar[s], pol);
+        }
+    }
+    __syncthreads();
+    const int cta = s_cta;
+    const long long lo = a.row_lo[cta];
+    const long long hi = a.row_lo[cta + 1];
+    const bool leader = (cta == 0 && tid == 0);
+    FosCtrl* C = e.ctrl;
+    const volatile FosCtrl* VC = C;
+
+    // column slice of this CTA (in column pairs)
+    const int pairs = e.ldv / 2;
+    const int pw = (pairs + P - 1) / P;                       // <= TAIL_PW (host-checked)
+    const int p0 = min(cta * pw, pairs);
+    const int npair = min(pw, pairs - p0);
+    const int NG = (P + TAIL_GS - 1) / TAIL_GS;
+    const int lane_ws = e.ldv + FOS_WIN_PAD;                  // doubles per (slot, source rank) in the push region
+
+    int slot = 0;
+    uint32_t parity = 0;
+    const unsigned long long gen0 = ld_acquire_gpu_u64(&gs->gen);   // passes this design's kernel has completed before
+    bool alive = true;
+    long long pass = 0;
+    if (leader) {
+        ts.acc_epi = VC->epi_ns;
+        ts.acc_xchg = VC->xchg_ns;
+        ts.acc_grad = VC->grad_ns;
+        ts.acc_passes = VC->n_passes;
+    }
+    for (; pass < max_passes; ++pass) {
+        // the state the leader committed before the last barrier of the previous pass (or the host, before
+        // the launch): one coalesced read per CTA, kept in shared memory for the tail of this pass
+        if (tid < 32) {
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(C);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ts.ctrl);
+            for (int w = tid; w < static_cast<int>(sizeof(FosCtrl) / 8); w += 32) dst[w] = __ldcg(src + w);
+        }
+        __syncthreads();
+        const int mode = ts.ctrl.g_mode;
+        if ((mode & (GM_GRAD | GM_DOT2)) == 0) break;
+        const unsigned long long gen = gen0 + static_cast<unsigned long long>(pass);
+        const unsigned long long target = (gen + 1ull) * static_cast<unsigned long long>(P);
+        const unsigned long long epoch = (e.world > 1) ? *reinterpret_cast<volatile unsigned long long*>(e.peer.epoch) : 0ull;
+        const unsigned long long t_pass0 = fos_globaltimer();
+        if (leader) ts.ctrl.pass_t0 = t_pass0;
+
+        // ---------------- the pass over this CTA's rows
+        const bool use_b = !(mode & GM_NOB);
+        if (LITE) {
+            stream_consume<T, NT, CPT, R, true, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
+        } else {
+            switch (mode & (GM_GRAD | GM_DOT2)) {
+                case GM_GRAD:
+                    stream_consume<T, NT, CPT, R, true, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
+                    break;
+                case GM_DOT2:
+                    stream_consume<T, NT, CPT, R, false, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
+                    break;
+                default:
+                    stream_consume<T, NT, CPT, R, true, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
+                    break;
+            }
+        }
+        // ---------------- barrier 1: all partials of this pass are in L2
+        const unsigned long long t_c1 = fos_globaltimer();
+        if (!grid_barrier(&gs->arrive0, target, gs, ts)) { alive = false; break; }
+        const unsigned long long t_b1 = fos_globaltimer();
+
+        const PgIn in = pg_read<false>(&ts.ctrl);
+        const int phase = in.phase;
+        const bool has_grad = (phase == PH_GRAD);
+        bool comm_ok = true;
+
+        // ---------------- local sums over the P partials: column slice (PH_GRAD) and residual norms (every CTA)
+        if (has_grad) {
+            for (int item = tid; item < npair * NG; item += NT) {
+                const int p = item % npair, q = item / npair;
+                const double* src = a.partial_g + static_cast<size_t>(q) * TAIL_GS * a.ldv + 2 * (p0 + p);
+                const int cnt = min(TAIL_GS, P - q * TAIL_GS);
+                double2 v[TAIL_GS];
+#pragma unroll
+                for (int u = 0; u < TAIL_GS; ++u)
+                    v[u] = (u < cnt) ? __ldcg(reinterpret_cast<const double2*>(src + static_cast<size_t>(u) * a.ldv))
+                                     : make_double2(0.0, 0.0);
+                double2 acc = v[0];
+#pragma unroll
+                for (int u = 1; u < TAIL_GS; ++u)
+                    if (u < cnt) {
+                        acc.x += v[u].x;
+                        acc.y += v[u].y;
+                    }
+                ts.gsum[q][p] = acc;
+            }
+        }
+        if (tid >= NT - 32 && tid - (NT - 32) < NG) {
+            const int q = tid - (NT - 32);
+            const int cnt = min(TAIL_GS, P - q * TAIL_GS);
+            const double* src = a.partial_s + static_cast<size_t>(q) * TAIL_GS * 2;
+            double2 v[TAIL_GS];   // all loads in flight before the first add (one L2 round trip, not eight)
+#pragma unroll
+            for (int u = 0; u < TAIL_GS; ++u)
+                v[u] = (u < cnt) ? __ldcg(reinterpret_cast<const double2*>(src + 2 * u)) : make_double2(0.0, 0.0);
+            double2 acc = v[0];
+#pragma unroll
+            for (int u = 1; u < TAIL_GS; ++u)
+                if (u < cnt) {
+                    acc.x += v[u].x;
+                    acc.y += v[u].y;
+                }
+            ts.ssum[q] = acc;
+        }
+        __syncthreads();
+        double2 gslice = make_double2(0.0, 0.0);   // thread tid < npair: its column pair of the (rank-local) gradient
+        if (has_grad && tid < npair) {
+            gslice = ts.gsum[0][tid];
+            for (int q = 1; q < NG; ++q) {
+                gslice.x += ts.gsum[q][tid].x;
+                gslice.y += ts.gsum[q][tid].y;
+            }
+        }
+        double s1 = 0.0, s2 = 0.0;
+        if (tid == NT - 1) {
+            double2 acc = ts.ssum[0];
+            for (int q = 1; q < NG; ++q) {
+                acc.x += ts.ssum[q].x;
+                acc.y += ts.ssum[q].y;
+            }
+            ts.s12[0] = acc.x;
+            ts.s12[1] = acc.y;
+        }
+        __syncthreads();
+        s1 = ts.s12[0];
+        s2 = ts.s12[1];
+
+        const unsigned long long t_s1 = fos_globaltimer();
+        // ---------------- row-sharded designs: slice exchange over peer memory
+        unsigned long long t_x0 = 0, t_x1 = 0;
+        if (e.world > 1) {
+            if (leader) t_x0 = fos_globaltimer();
+            const size_t slot_off = static_cast<size_t>(epoch & 1ull) * FOS_MAX_WORLD * lane_ws;
+            const size_t mine = slot_off + static_cast<size_t>(e.rank) * lane_ws;
+            if (has_grad && tid < npair) {
+                for (int r = 0; r < e.world; ++r) st_relaxed_sys_v2(e.peer.fwin[r] + mine + 2 * (p0 + tid), gslice);
+            }
+            if (cta == 0 && tid == NT - 1) {
+                for (int r = 0; r < e.world; ++r) st_relaxed_sys_v2(e.peer.fwin[r] + mine + e.ldv, make_double2(s1, s2));
+            }
+            __syncthreads();
+            // CTAs that pushed something signal (rank, CTA); everybody else only listens to CTA 0's flags
+            const bool pushed = (has_grad && npair > 0) || cta == 0;
+            if (pushed && tid < e.world) {
+                __threadfence_system();
+                st_release_sys_u64(e.peer.fflag[tid] + static_cast<size_t>(e.rank) * FOS_MAX_PARTS + cta, epoch);
+            }
+            if (tid == 0) ts.ok = 1;
+            __syncthreads();
+            if (tid < e.world) {
+                // my slice from rank `tid` (only when there is one), and the scalars from its CTA 0
+                const unsigned long long* f_own = e.peer.fflag[e.rank] + static_cast<size_t>(tid) * FOS_MAX_PARTS + cta;
+                const unsigned long long* f_sc = e.peer.fflag[e.rank] + static_cast<size_t>(tid) * FOS_MAX_PARTS;
+                const bool need_own = has_grad && npair > 0;
+                const unsigned long long t0 = fos_globaltimer();
+                unsigned spins = 0;
+                while ((need_own && ld_acquire_sys_u64(f_own) < epoch) || ld_acquire_sys_u64(f_sc) < epoch) {
+                    if ((++spins & 1023u) == 0u) {
+                        if (*reinterpret_cast<volatile int*>(&gs->abort) != 0 || fos_globaltimer() - t0 > PEER_WAIT_NS) {
+                            atomicExch(&gs->abort, 1);
+                            ts.ok = 0;
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            comm_ok = ts.ok != 0;
+            if (comm_ok) {
+                if (has_grad && tid < npair) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    double2 v[FOS_MAX_WORLD];
+#pragma unroll
+                    for (int r = 0; r < FOS_MAX_WORLD; ++r)
+                        if (r < e.world)
+                            v[r] = ld_relaxed_sys_v2(e.peer.fwin[e.rank] + slot_off + static_cast<size_t>(r) * lane_ws + 2 * (p0 + tid));
+#pragma unroll
+                    for (int r = 0; r < FOS_MAX_WORLD; ++r)
+                        if (r < e.world) {
+                            acc.x += v[r].x;
+                            acc.y += v[r].y;
+                        }
+                    gslice = acc;
+                }
+                if (tid == NT - 1) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int r = 0; r < e.world; ++r) {
+                        const double2 v = ld_relaxed_sys_v2(e.peer.fwin[e.rank] + slot_off + static_cast<size_t>(r) * lane_ws + e.ldv);
+                        acc.x += v.x;
+                        acc.y += v.y;
+                    }
+                    ts.s12[0] = acc.x;
+                    ts.s12[1] = acc.y;
+                }
+            }
+            __syncthreads();
+            s1 = ts.s12[0];
+            s2 = ts.s12[1];
+            if (leader) t_x1 = fos_globaltimer();
+        }
+
+        const unsigned long long t_x2 = fos_globaltimer();
+        // ---------------- elementwise 1 on the slice + slice sums
+        bool accept;
+        double t_new;
+        pg_armijo(in, s2, accept, t_new);
+        double sums[FOS_NSCAL];
+#pragma unroll
+        for (int k = 0; k < FOS_NSCAL; ++k) sums[k] = 0.0;
+        if (tid < npair) {
+            const int c = 2 * (p0 + tid);
+            if (phase == PH_GRAD) pg_elem1_grad<true>(e, in, c, gslice, sums);
+            else if (phase == PH_TRIAL) pg_elem1_trial<true>(e, in, c, accept, t_new, sums);
+        }
+        if (tid < TAIL_PW) {
+#pragma unroll
+            for (int k = 0; k < FOS_NSCAL; ++k) ts.red[k][tid] = sums[k];
+        }
+        __syncthreads();
+        if (tid < FOS_NSCAL) {
+            double t = 0.0;
+            for (int p = 0; p < npair; ++p) t += ts.red[tid][p];
+            gs->scal[cta][tid] = t;
+        }
+        // ---------------- barrier 2: every CTA's slice sums are in L2
+        const unsigned long long t_e1 = fos_globaltimer();
+        if (!grid_barrier(&gs->arrive1, target, gs, ts)) { alive = false; break; }
+        const unsigned long long t_b2 = fos_globaltimer();
+        for (int item = tid; item < NG * FOS_NSCAL; item += NT) {
+            const int k = item % FOS_NSCAL, q = item / FOS_NSCAL;
+            const int cnt = min(TAIL_GS, P - q * TAIL_GS);
+            double v[TAIL_GS];
+#pragma unroll
+            for (int u = 0; u < TAIL_GS; ++u) v[u] = (u < cnt) ? __ldcg(&gs->scal[q * TAIL_GS + u][k]) : 0.0;
+            double t = v[0];
+#pragma unroll
+            for (int u = 1; u < TAIL_GS; ++u)
+                if (u < cnt) t += v[u];
+            ts.grp[q][k] = t;
+        }
+        __syncthreads();
+        if (tid < FOS_NSCAL) {
+            double t = 0.0;
+            for (int q = 0; q < NG; ++q) t += ts.grp[q][tid];
+            ts.tot[tid] = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FOS_NSCAL; ++k) sums[k] = ts.tot[k];
+
+        // ---------------- scalar logic (identical everywhere), elementwise 2 on the slice, commit
+        const PgOut o = pg_decide(in, sums, s1, s2, accept, t_new);
+        if (o.do_update && tid < npair) pg_elem2<true>(e, in, o, 2 * (p0 + tid));
+        if (leader) {
+            if (e.world > 1) *e.peer.epoch = epoch + 1;
+            ts.acc_grad += t_b1 - t_pass0;
+            ts.acc_epi += fos_globaltimer() - t_b1;
+            ts.acc_xchg += t_x1 - t_x0;
+            ts.acc_passes += 1;
+            pg_commit<true>(C, e.hist, in, o, comm_ok, t_b1, 0ull);
+            C->grad_ns = ts.acc_grad;
+            C->epi_ns = ts.acc_epi;
+            C->xchg_ns = ts.acc_xchg;
+            C->n_passes = ts.acc_passes;
+            gs->gen = gen + 1ull;
+        }
+        // ---------------- barrier 3: y, x_k and the control block are complete before anyone starts the next pass
+        const unsigned long long t_e2 = fos_globaltimer();
+        if (!grid_barrier(&gs->arrive2, target, gs, ts)) { alive = false; break; }
+        if (leader) {
+            const unsigned long long t_b3 = fos_globaltimer();
+            gs->prof[0] += t_c1 - t_pass0;
+            gs->prof[1] += t_b1 - t_c1;
+            gs->prof[2] += t_s1 - t_b1;
+            gs->prof[3] += t_x2 - t_s1;
+            gs->prof[4] += t_e1 - t_x2;
+            gs->prof[5] += t_b2 - t_e1;
+            gs->prof[6] += t_e2 - t_b2;
+            gs->prof[7] += t_b3 - t_e2;
+            gs->prof[8] += 1;
+        }
+        if (!comm_ok) break;
+    }
+
+    // drain the copies still in flight (the first stages of a pass that will not run here)
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) {
+            mbar_wait(&sm.full_bar[slot], parity);
+            if (++slot == nstage) {
+                slot = 0;
+                parity ^= 1u;
+            }
+        }
+    }
+    if (!alive && leader) {  // abandoned: the host reports the error (FOS_ERR_COMM)
+        C->stop_reason = -1;
+        C->phase = PH_DONE;
+        C->g_mode = GM_SKIP;
     }
 }
 
@@ -861,6 +1326,7 @@ grad_generic_kernel(GradArgs a) {
 struct StreamCfg {
     const void* fn;
     int nt, cpt, r;
+    const void* solve_fn = nullptr;  // persistent solve kernel of the same shape (full-mode builds only)
 };
 
 // FOS_SKEW=1/0: the software-pipelined consumer loop (stream_consume_skew) or the plain one
@@ -874,9 +1340,14 @@ bool use_skew() {
 
 template <typename T, int NT, int CPT, int R, bool LITE = false>
 StreamCfg make_cfg() {
-    if (use_skew())
-        return StreamCfg{reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, true>), NT, CPT, R};
-    return StreamCfg{reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, false>), NT, CPT, R};
+    StreamCfg c;
+    c.fn = use_skew() ? reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, true>)
+                      : reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, false>);
+    c.nt = NT;
+    c.cpt = CPT;
+    c.r = R;
+    if (!LITE) c.solve_fn = reinterpret_cast<const void*>(&solve_stream_kernel<T, NT, CPT, R, false>);
+    return c;
 }
 
 // gradient-only variant for wide rows, if one exists
@@ -940,6 +1411,31 @@ int fos_grad_plan(fos_design* h) {
         if (h->n < h->sm_count) h->n_parts = static_cast<int>(h->n > 0 ? h->n : 1);
         FOS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SMEM_RING_BUDGET));
+        // The persistent solve kernel needs: one CTA per SM (all co-resident), every CTA's row block at
+        // least as long as the ring (the ring wraps into the next pass), column slices of at most
+        // TAIL_PW pairs.  FOS_FUSED=0 keeps the two-launch path (A/B, debugging).
+        {
+            const char* ff = getenv("FOS_FUSED");
+            const int elem = (h->dtype == FOS_F64) ? 8 : 4;
+            int sb = (cfg.r * h->lda * elem + 127) & ~127;
+            int ns = std::min(SMEM_RING_BUDGET / sb, MAX_STAGES);
+            const int pairs = h->ldv / 2;
+            // (the ring depth is fitted to the shortest row block at launch time, fos_solve_stages)
+            h->fused_ok = !(ff && ff[0] == '0') && cfg.solve_fn != nullptr && h->n_parts == h->sm_count &&
+                          h->n_parts <= FOS_MAX_PARTS && ns >= 2 && h->n / h->n_parts >= 2LL * cfg.r &&
+                          (pairs + h->n_parts - 1) / h->n_parts <= TAIL_PW;
+            if (h->fused_ok) {
+                int max_blocks = 0;
+                cudaError_t ce = cudaFuncSetAttribute(cfg.solve_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RING_BUDGET);
+                if (ce == cudaSuccess)
+                    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, cfg.solve_fn, cfg.nt,
+                                                                       static_cast<size_t>(ns) * sb);
+                if (ce != cudaSuccess || max_blocks < 1) {
+                    cudaGetLastError();
+                    h->fused_ok = false;
+                }
+            }
+        }
         StreamCfg lite;
         const char* nl = getenv("FOS_NO_LITE");
         h->lite_ok = pick_lite_cfg(h->dtype, h->lda, &lite) && !(nl && nl[0] == '1');
@@ -951,6 +1447,74 @@ int fos_grad_plan(fos_design* h) {
         long long cap = static_cast<long long>(h->sm_count) * 4;
         h->n_parts = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
     }
+    return FOS_OK;
+}
+
+// Ring depth of the persistent kernel for this design's current row partition: as deep as the
+// shared-memory budget allows, but never deeper than the shortest row block has stages (the ring
+// wraps from the end of a pass into the start of the next one).  0: the design does not qualify.
+int fos_solve_stages(const fos_design* h) {
+    if (!h->fused_ok || h->kern_kind != 1 || h->gsync == nullptr) return 0;
+    StreamCfg cfg;
+    if (!pick_stream_cfg(h->dtype, h->lda, &cfg)) return 0;
+    const int elem = (h->dtype == FOS_F64) ? 8 : 4;
+    const int stage_bytes = (cfg.r * h->lda * elem + 127) & ~127;
+    long long min_rows = h->n;
+    for (int c = 0; c < h->n_parts; ++c) min_rows = std::min(min_rows, h->row_lo_host[c + 1] - h->row_lo_host[c]);
+    const long long ns = std::min<long long>(std::min(SMEM_RING_BUDGET / stage_bytes, MAX_STAGES), min_rows / cfg.r);
+    return ns >= 2 ? static_cast<int>(ns) : 0;
+}
+
+int fos_launch_solve(fos_design* h, const FosHist& hist, long long max_passes) {
+    int nstage = fos_solve_stages(h);
+    if (nstage == 0) {
+        fos_set_error("this design does not qualify for the persistent solve kernel");
+        return FOS_ERR_UNSUPPORTED;
+    }
+    StreamCfg cfg;
+    pick_stream_cfg(h->dtype, h->lda, &cfg);
+    GradArgs a;
+    a.A = h->A;
+    a.b = h->b;
+    a.v1 = h->y;
+    a.v2 = h->xc;
+    a.partial_g = h->partial_g;
+    a.partial_s = h->partial_s;
+    a.ctrl = h->ctrl;
+    a.n = h->n;
+    a.d = h->d;
+    a.lda = h->lda;
+    a.ldv = h->ldv;
+    a.mode_override = -1;
+    a.cta_times = nullptr;
+    a.row_lo = h->row_lo;
+    a.sm_slot = h->sm_slot;
+    a.slot_claim = a.sm_slot ? reinterpret_cast<unsigned*>(h->sm_slot + 256) : nullptr;
+    a.pass_no = static_cast<unsigned>(h->launches & 0x7fffffff);
+    EpiArgs e{};
+    e.ctrl = h->ctrl;
+    e.hist = hist;
+    e.partial_g = h->partial_g;
+    e.partial_s = h->partial_s;
+    e.n_parts = h->n_parts;
+    e.d = h->d;
+    e.ldv = h->ldv;
+    e.op = EOP_PG;
+    e.y = h->y;
+    e.xc = h->xc;
+    e.xk = h->xk;
+    e.g = h->g;
+    e.world = h->world;
+    e.rank = h->rank;
+    e.peer = h->peer;
+    const int elem = (h->dtype == FOS_F64) ? 8 : 4;
+    int stage_bytes = (cfg.r * h->lda * elem + 127) & ~127;
+    FosGridSync* gs = h->gsync;
+    void* params[6] = {&a, &e, &gs, &stage_bytes, &nstage, &max_passes};
+    // cooperative launch: the driver refuses the launch unless all CTAs can be resident at once
+    FOS_CUDA(fos_launch_ex(cfg.solve_fn, dim3(h->n_parts), dim3(cfg.nt), static_cast<size_t>(nstage) * stage_bytes,
+                           h->stream, params, false, -1));
+    h->launches++;
     return FOS_OK;
 }
 

@@ -132,6 +132,11 @@ int fos_design_set_profile(fos_design* h, int enable);
 int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms_avg);
 /* Debug: per-CTA start/end timestamps (ns) of one gradient-kernel launch; out[2*n_parts]. */
 int fos_debug_cta_times(fos_design* h, int mode, long long* out, int cap, int* n_parts);
+/* Debug: phase profile of the persistent solve kernel (CTA 0's %globaltimer stamps, ns, accumulated
+ * since the design was created): out[0..7] = streaming loop, wait at barrier 1, slice sums, peer exchange,
+ * elementwise 1, barrier 2, scalars + decision + elementwise 2 + commit, barrier 3; out[8] = passes.
+ * reset != 0 zeroes the accumulators after reading.  All zeros for designs that never ran it. */
+int fos_debug_solve_profile(fos_design* h, unsigned long long* out9, int reset);
 /* lambda_max = ||A^T b||_inf (one fused pass), the usual scale for alpha1 */
 int fos_design_lambda_max(fos_design* h, double* out);
 

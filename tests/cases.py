@@ -28,6 +28,10 @@ DESIGNS = {
     # backtracking, steep / shallow Armijo factors, non-zero ISTA start, capped L-BFGS).  Runs against
     # the oracle and the host layer on the CPU and against the kernels in the GPU suite.
     "midx": dict(store=False),
+    # 2400 x 600, the same off-grid option combinations on a design wide and tall enough for the
+    # streaming kernel AND the persistent solve kernel (16 rows per CTA): restarts, ratio / step /
+    # gradient-norm stops, steep and shallow Armijo factors, non-zero ISTA start inside ONE launch
+    "widex": dict(store=False),
 }
 
 
@@ -72,6 +76,8 @@ def design(name):
         return _elementwise_design(1500, 640, 13, 2.0)
     if name == "midx":
         return _elementwise_design(2000, 64, 21, 0.8)
+    if name == "widex":
+        return _elementwise_design(2400, 600, 23, 1.0)
     raise KeyError(name)
 
 
@@ -88,7 +94,7 @@ def solver_specs(name, A, b):
     them back so both sides see identical scalars."""
     lam = float(np.max(np.abs(np.asarray(A, dtype=np.float64).T @ b)))
     a1 = 0.1 * lam
-    if name == "midx":
+    if name in ("midx", "widex"):
         return _extra_specs(lam)
     regs = {"lasso": (a1, 0.0), "elasticnet": (a1, 0.5 * a1)}
     specs = {}

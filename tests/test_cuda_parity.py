@@ -121,6 +121,75 @@ def test_prox_gradient_traces(be, name, key):
     harness.check_case(out, spec, name, key, rtol)
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("fista", "fista_delta", "ista"),
+                                                            designs=("wide", "widex")))
+def test_persistent_solve_kernel_and_two_launch_path(be, name, key, fused, monkeypatch):
+    """The streaming designs run every solve as ONE launch of the persistent kernel (gradient pass,
+    in-kernel cross-CTA reduction, prox / momentum / stop rules on column slices, three grid barriers
+    per pass); FOS_FUSED=0 keeps the (gradient, epilogue) launch pairs.  Both against the same golden
+    traces of the reference, and the launch count says which one ran."""
+    from fastoptsolver_b200 import iterative_solvers as S
+    monkeypatch.setenv("FOS_FUSED", fused)
+    out, spec = harness.run_case(be, name, key)
+    harness.check_case(out, spec, name, key, RTOL_F64)
+    info = S.last_run["solver"]
+    if info["passes"] > 0:
+        assert (info["kernel_launches"] == 1) == (fused == "1"), info
+
+
+def test_persistent_solve_kernel_at_scale(monkeypatch):
+    """200 000 x 2048 (1351 rows per CTA, ring of 6 stages wrapping from pass to pass): the persistent
+    kernel and the two-launch path give the same iterates (1e-12: the cross-CTA sums associate
+    differently), the same objective traces and Armijo counts; two runs of the persistent kernel are
+    bit-identical."""
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200.design import DeviceDesign
+    des = DeviceDesign.synthetic(200_000, 2048, seed=3, noise_std=0.5, rho1=0.5, rho2=0.7)
+    a1 = 0.05 * des.lambda_max()
+    np.random.seed(0)
+    L = S.estimate_lipschitz(des)
+    variants = [
+        ("fista", dict(max_iter=30)),
+        ("fista", dict(max_iter=25, backtracking=True, t_init_factor=3.0)),
+        ("fista", dict(max_iter=60, adaptive_restart=True, restart_threshold=0.9)),
+        ("fista", dict(max_iter=400, tol_ratio=0.3)),        # fires at iteration 6 (ratio 0.2505)
+        ("fista_delta", dict(max_iter=25, backtracking=True, t_init_factor=2.0, eta=0.7)),
+    ]
+    for kind, kw in variants:
+        res = {}
+        for fused in ("1", "0", "1"):
+            monkeypatch.setenv("FOS_FUSED", fused)
+            d2 = DeviceDesign.from_device_pointers(*des_pointers(des), des.shape[0], des.shape[1], des.dtype, des.shape[1],
+                                                   keepalive=des)
+            np.random.seed(0)
+            if kind == "fista":
+                x, h = S.fista(d2, None, "elasticnet", a1, 0.01 * a1, return_history=True, **kw)
+            else:
+                x, h = S.fista_delta(d2, None, "elasticnet", a1, 0.01 * a1, 3.0, return_history=True, **kw)
+            info = dict(S.last_run["solver"])
+            assert (info["kernel_launches"] == 1) == (fused == "1")
+            res.setdefault(fused, []).append((x, h, list(S.ls_call_iters), info["iters"]))
+            d2.close()
+        (xa, ha, lsa, ita), (xb, hb, lsb, itb) = res["1"][0], res["0"][0]
+        assert ita == itb and lsa == lsb, (kind, kw)
+        assert harness.rel_err(xa, xb) <= 1e-12
+        assert harness.rel_err(ha["obj"], hb["obj"]) <= 1e-12
+        for u, v in zip(ha["x"], hb["x"]):
+            assert np.linalg.norm(u - v) <= 1e-12 * max(np.linalg.norm(v), 1e-300) + 1e-300
+        xc, hc, lsc, itc = res["1"][1]
+        assert xc.tobytes() == xa.tobytes() and np.asarray(hc["obj"]).tobytes() == np.asarray(ha["obj"]).tobytes()
+    des.close()
+
+
+def des_pointers(des):
+    import ctypes as C
+    from fastoptsolver_b200 import _lib
+    a, b = C.c_void_p(), C.c_void_p()
+    _lib.check(_lib.load().fos_design_pointers(des.handle, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 @pytest.mark.parametrize("name,key", harness.all_case_ids(solvers=("lbfgs",)))
 def test_lbfgs_traces(be, name, key):
     out, spec = harness.run_case(be, name, key)

@@ -29,7 +29,9 @@ def _free_port():
 
 CASES = [("wide", "fista/lasso-fixed-t1.0"), ("wide", "fista/lasso-armijo-t2.0"),
          ("mid", "fista_delta/elasticnet-armijo-t2.0"), ("mid", "ista/lasso-armijo-t2.0"),
-         ("mid", "lbfgs/ridge"), ("odd", "fista/lasso-armijo-t2.0"), ("mid", "fista/lasso-tol")]
+         ("mid", "lbfgs/ridge"), ("odd", "fista/lasso-armijo-t2.0"), ("mid", "fista/lasso-tol"),
+         # 1200 rows per rank at world 2: the persistent solve kernel with its push-model slice exchange
+         ("widex", "fista/restart-armijo"), ("widex", "fista_delta/step-stop"), ("widex", "ista/nonzero-start-armijo")]
 
 
 def _worker(rank, world, port, q):
