@@ -820,7 +820,8 @@ __device__ __forceinline__ bool grid_barrier(unsigned long long* ctr, unsigned l
                                              TailSmem& ts) {
     __syncthreads();  // every thread's writes of this phase are ordered before thread 0's release
     if (threadIdx.x == 0) {
-        __threadfence();
+        // release / acquire at gpu scope on the counter itself (cumulative over the CTA's writes through the
+        // bar.sync above; the readers bypass L1 with ld.cg): no MEMBAR on either side
         red_release_gpu_add(ctr, 1ull);
         bool ok = true;
         if (ld_acquire_gpu_u64(ctr) < target) {
@@ -836,7 +837,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned long long* ctr, unsigned l
                 }
             }
         }
-        __threadfence();
         ts.ok = ok ? 1 : 0;
     }
     __syncthreads();
@@ -913,15 +913,16 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
         ts.acc_grad = VC->grad_ns;
         ts.acc_passes = VC->n_passes;
     }
+    // the state the host wrote before the launch: one coalesced read per CTA into shared memory.  From
+    // here on every CTA keeps its copy current itself -- the decision of a pass is computed identically
+    // in every CTA -- so the control block in HBM is only written (by CTA 0, for the host), never re-read.
+    if (tid < 32) {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(C);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ts.ctrl);
+        for (int w = tid; w < static_cast<int>(sizeof(FosCtrl) / 8); w += 32) dst[w] = __ldcg(src + w);
+    }
+    __syncthreads();
     for (; pass < max_passes; ++pass) {
-        // the state the leader committed before the last barrier of the previous pass (or the host, before
-        // the launch): one coalesced read per CTA, kept in shared memory for the tail of this pass
-        if (tid < 32) {
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(C);
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(&ts.ctrl);
-            for (int w = tid; w < static_cast<int>(sizeof(FosCtrl) / 8); w += 32) dst[w] = __ldcg(src + w);
-        }
-        __syncthreads();
         const int mode = ts.ctrl.g_mode;
         if ((mode & (GM_GRAD | GM_DOT2)) == 0) break;
         const unsigned long long gen = gen0 + static_cast<unsigned long long>(pass);
@@ -1100,10 +1101,11 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
         double sums[FOS_NSCAL];
 #pragma unroll
         for (int k = 0; k < FOS_NSCAL; ++k) sums[k] = 0.0;
+        double2 cand = make_double2(0.0, 0.0), xk = make_double2(0.0, 0.0);   // stay in registers for elementwise 2
         if (tid < npair) {
             const int c = 2 * (p0 + tid);
-            if (phase == PH_GRAD) pg_elem1_grad<true>(e, in, c, gslice, sums);
-            else if (phase == PH_TRIAL) pg_elem1_trial<true>(e, in, c, accept, t_new, sums);
+            if (phase == PH_GRAD) pg_elem1_grad<true>(e, in, c, gslice, sums, &cand, &xk);
+            else if (phase == PH_TRIAL) pg_elem1_trial<true>(e, in, c, accept, t_new, sums, &cand, &xk);
         }
         if (tid < TAIL_PW) {
 #pragma unroll
@@ -1143,7 +1145,8 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
 
         // ---------------- scalar logic (identical everywhere), elementwise 2 on the slice, commit
         const PgOut o = pg_decide(in, sums, s1, s2, accept, t_new);
-        if (o.do_update && tid < npair) pg_elem2<true>(e, in, o, 2 * (p0 + tid));
+        if (o.do_update && tid < npair) pg_elem2_regs(e, in, o, 2 * (p0 + tid), cand, xk);
+        if (tid == 0) pg_apply_state(&ts.ctrl, o, comm_ok);   // this CTA's copy: what the next pass starts from
         if (leader) {
             if (e.world > 1) *e.peer.epoch = epoch + 1;
             ts.acc_grad += t_b1 - t_pass0;

@@ -81,7 +81,8 @@ __device__ __forceinline__ void pg_armijo(const PgIn& in, double s2, bool& accep
 
 // ---- elementwise 1 (PH_GRAD): gradient (+a2 y), candidate point, local sums; g = reduced A^T r
 template <bool CG>
-__device__ __forceinline__ void pg_elem1_grad(const EpiArgs& e, const PgIn& in, int c, double2 g, double (&sums)[FOS_NSCAL]) {
+__device__ __forceinline__ void pg_elem1_grad(const EpiArgs& e, const PgIn& in, int c, double2 g, double (&sums)[FOS_NSCAL],
+                                              double2* cand_out = nullptr, double2* xk_out = nullptr) {
     const double2 y = pg_ld2<CG>(e.y + c);
     const double2 xk = pg_ld2<CG>(e.xk + c);
     if (in.a2 > 0.0) {
@@ -100,12 +101,15 @@ __device__ __forceinline__ void pg_elem1_grad(const EpiArgs& e, const PgIn& in, 
     sums[S_XX] = fma(cand.y, cand.y, fma(cand.x, cand.x, sums[S_XX]));
     sums[S_GD] = fma(g.y, cand.y - y.y, fma(g.x, cand.x - y.x, sums[S_GD]));
     sums[S_YY] = fma(y.y, y.y, fma(y.x, y.x, sums[S_YY]));
+    if (cand_out) *cand_out = cand;
+    if (xk_out) *xk_out = xk;
 }
 
 // ---- elementwise 1 (PH_TRIAL): keep the accepted candidate or form the next one with the shrunk step
 template <bool CG>
 __device__ __forceinline__ void pg_elem1_trial(const EpiArgs& e, const PgIn& in, int c, bool accept, double t_new,
-                                               double (&sums)[FOS_NSCAL]) {
+                                               double (&sums)[FOS_NSCAL], double2* cand_out = nullptr,
+                                               double2* xk_out = nullptr) {
     const double2 xk = pg_ld2<CG>(e.xk + c);
     double2 cand;
     if (accept) {
@@ -122,6 +126,8 @@ __device__ __forceinline__ void pg_elem1_trial(const EpiArgs& e, const PgIn& in,
     sums[S_DX2] = fma(dy, dy, fma(dx, dx, sums[S_DX2]));
     sums[S_L1] += fabs(cand.x) + fabs(cand.y);
     sums[S_XX] = fma(cand.y, cand.y, fma(cand.x, cand.x, sums[S_XX]));
+    if (cand_out) *cand_out = cand;
+    if (xk_out) *xk_out = xk;
 }
 
 // everything the scalar logic decides (identical in every thread that runs it)
@@ -242,11 +248,14 @@ __device__ __forceinline__ PgOut pg_decide(const PgIn& in, const double (&sums)[
 }
 
 // ---- elementwise 2: momentum point, roll the iterate, history row (only when o.do_update)
+// (the candidate and the current iterate of the column pair: still in the caller's registers, or re-read)
+__device__ __forceinline__ void pg_elem2_regs(const EpiArgs& e, const PgIn& in, const PgOut& o, int c, double2 cand, double2 xk);
 template <bool CG>
 __device__ __forceinline__ void pg_elem2(const EpiArgs& e, const PgIn& in, const PgOut& o, int c) {
+    pg_elem2_regs(e, in, o, c, pg_ld2<CG>(e.xc + c), pg_ld2<CG>(e.xk + c));
+}
+__device__ __forceinline__ void pg_elem2_regs(const EpiArgs& e, const PgIn& in, const PgOut& o, int c, double2 cand, double2 xk) {
     double* hrow = (e.hist.x_hist != nullptr) ? e.hist.x_hist + static_cast<size_t>(in.k + 1) * e.d : nullptr;
-    const double2 cand = pg_ld2<CG>(e.xc + c);
-    const double2 xk = pg_ld2<CG>(e.xk + c);
     double2 yn;
     if (o.plain_copy) {
         yn = cand;
@@ -260,6 +269,32 @@ __device__ __forceinline__ void pg_elem2(const EpiArgs& e, const PgIn& in, const
         if (c < e.d) hrow[c] = cand.x;
         if (c + 1 < e.d) hrow[c + 1] = cand.y;
     }
+}
+
+// ---- the dynamic state the next pass starts from (the persistent kernel applies it to every CTA's
+// shared-memory copy of the control block as well: the decision is identical everywhere)
+__device__ __forceinline__ void pg_apply_state(FosCtrl* C, PgOut o, bool comm_ok) {
+    if (!comm_ok) {  // a peer never arrived: abort the solve, the host reports FOS_ERR_COMM
+        o.n_phase = PH_DONE;
+        o.n_gmode = GM_SKIP;
+        o.n_stop = -1;
+    }
+    C->phase = o.n_phase;
+    C->g_mode = o.n_gmode;
+    C->k = o.n_k;
+    C->shrinks = o.n_shrinks;
+    C->obj_pending = o.n_obj_pending;
+    C->stop_reason = o.n_stop;
+    C->n_grad_calls = o.n_ngrad;
+    C->tau = o.n_tau;
+    C->trial_t = o.n_trial;
+    C->gy = o.n_gy;
+    C->gd = o.n_gd;
+    C->cand_xx = o.n_cxx;
+    C->pend_l2 = o.n_pl2;
+    C->pend_l1 = o.n_pl1;
+    C->t_mom = o.n_tmom;
+    C->prev_step = o.n_prev;
 }
 
 // ---- the one thread that owns the control block writes the new state and the history scalars
@@ -282,28 +317,8 @@ __device__ __forceinline__ void pg_commit(FosCtrl* C, const FosHist& hist, const
         C->epi_ns += fos_globaltimer() - t_epi0;
         C->xchg_ns += xchg_ns;
     }
-    if (!comm_ok) {  // a peer never arrived: abort the solve, the host reports FOS_ERR_COMM
-        o.n_phase = PH_DONE;
-        o.n_gmode = GM_SKIP;
-        o.n_stop = -1;
-    }
-    C->phase = o.n_phase;
-    C->g_mode = o.n_gmode;
-    C->k = o.n_k;
-    C->shrinks = o.n_shrinks;
-    C->obj_pending = o.n_obj_pending;
-    C->stop_reason = o.n_stop;
-    C->n_grad_calls = o.n_ngrad;
     if (!TOTALS_BY_CALLER) C->n_passes += 1;
-    C->tau = o.n_tau;
-    C->trial_t = o.n_trial;
-    C->gy = o.n_gy;
-    C->gd = o.n_gd;
-    C->cand_xx = o.n_cxx;
-    C->pend_l2 = o.n_pl2;
-    C->pend_l1 = o.n_pl1;
-    C->t_mom = o.n_tmom;
-    C->prev_step = o.n_prev;
+    pg_apply_state(C, o, comm_ok);
 }
 
 }  // namespace
