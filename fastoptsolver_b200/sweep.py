@@ -108,6 +108,14 @@ def suboptimality(traces):
             for p, panel in traces.items()}
 
 
+def suboptimality_own(traces):
+    """f(x_k) - min_k f(x_k) per curve: every curve against its OWN best value -- the convention the
+    reference's figures evidently use (each curve of figures/benchmark_*.png drops to zero at its own
+    last iterate; L-BFGS, which never sees the L1 term, and the stalled Armijo runs included)."""
+    return {p: {lab: [max(v - float(np.min(tr)), 0.0) for v in tr] if len(tr) else [] for lab, tr in panel.items()}
+            for p, panel in traces.items()}
+
+
 def first_below(sub, level=1e-5):
     """{panel: {curve: first iteration (1-based) with suboptimality < level, or None}}."""
     out = {}
@@ -140,6 +148,9 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--source", default="device", choices=["device", "reference"],
                     help="device: Philox generator in HBM; reference: the reference's host generator + z-scoring")
+    ap.add_argument("--raw", action="store_true", help="device source: do not z-score the columns / centre b")
+    ap.add_argument("--csv-first", type=int, default=0,
+                    help="write the per-iteration CSV only for the first N scenarios (0: all); the summary covers all")
     args = ap.parse_args(argv)
     os.makedirs(args.out, exist_ok=True)
     summary = []
@@ -155,12 +166,16 @@ def main(argv=None):
             des = DeviceDesign.from_host(A.astype(dt), b, device=args.device)
         else:
             des = DeviceDesign.synthetic(args.n, args.d, dt, device=args.device, **sc)
+            if not args.raw:
+                des.standardize()      # what the notebook did to its data on the host
         traces, timing, meta = run_scenario(des, max_iter=args.max_iter)
         sub = suboptimality(traces)
-        write_csv(os.path.join(args.out, f"benchmark_{name}.csv"), sub)
+        if not args.csv_first or i < args.csv_first:
+            write_csv(os.path.join(args.out, f"benchmark_{name}.csv"), sub)
         rec = {"scenario": name, "n": args.n, "d": args.d, "source": args.source, **meta, "seconds": timing["total_s"],
                "iters": {p: {k: len(v) for k, v in c.items()} for p, c in traces.items()},
-               "iters_to_1e-5": first_below(sub)}
+               "iters_to_1e-5": first_below(sub), "iters_to_1e-5_own_best": first_below(suboptimality_own(traces)),
+               "first_suboptimality": {p: {k: (v[0] if len(v) else None) for k, v in c.items()} for p, c in sub.items()}}
         summary.append(rec)
         print(json.dumps(rec), flush=True)
         des.close()
