@@ -84,17 +84,51 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.t0 = None
+        self.nvml = None
+        self._stop = False
+        self.source = None
 
     def start(self):
+        # in-process NVML at 10 Hz (four light queries per sample); the nvidia-smi -lms subprocess is the
+        # fallback.  Either way the first sample is awaited before anything is timed (wait_first_sample).
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                     "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+                self.thread = threading.Thread(target=self._read, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.proc = None
         self.t0 = time.perf_counter()
+
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = int(get_reasons(h))
+                self.rows.append(", ".join([str(sm), str(mx), f"{pw:.2f}"] +
+                                           [("Active" if rs & b else "Not Active") for _, b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -106,7 +140,7 @@ class ClockSampler:
         meanwhile (r2: 197 it/s in a timed region that overlapped it, 213-224 it/s for the identical
         solves that followed), so it must be over before the timed region begins."""
         t = time.perf_counter()
-        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+        while (self.proc is not None or self.nvml is not None) and not self.rows and time.perf_counter() - t < timeout:
             time.sleep(0.01)
         self.t0 = time.perf_counter()
 
@@ -114,15 +148,17 @@ class ClockSampler:
         return time.perf_counter() - self.t0 if self.t0 else 0.0
 
     def stop(self, covers=()):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.proc is None and self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
         window = self.elapsed()
         time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons, pw = [], [], {}, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -141,7 +177,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
                 "power_w_median": float(np.median(pw)) if pw else None, "samples": len(sm),
-                "window_s": window, "period_ms": 100, "covers": list(covers), "reasons": sorted(reasons),
+                "window_s": window, "period_ms": 100, "source": self.source, "covers": list(covers), "reasons": sorted(reasons),
                 "reason_samples": reasons}
 
 

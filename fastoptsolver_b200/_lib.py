@@ -131,6 +131,7 @@ SIGNATURES = {
     "fos_gram_subset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "fos_gram_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fos_gram_path_fista": (C.c_int, [C.c_void_p, C.POINTER(PathParams), C.POINTER(PathResult)]),
+    "fos_mrhs_fista": (C.c_int, [C.c_void_p, C.POINTER(PathParams), C.POINTER(PathResult)]),
 }
 
 _lib = None

@@ -1,0 +1,502 @@
+// mrhs_kernels.cu -- streaming multi-RHS mode (north_star item 4: "A^T A and A X really are dense
+// contractions"): fixed-step FISTA for a whole batch of L1 penalties WITHOUT the Gram matrix, for
+// designs where d^2 does not fit or n is not >> d.  Per iteration and per batch of 8 penalties A is
+// streamed from HBM ONCE and both contractions run on the fp64 tensor pipe (mma.sync.m8n8k4.f64;
+// tcgen05 has no f64 kind):
+//
+//     U = A Y - b 1^T        (rows x 8)     D[8 rows x 8 lambda] += A_tile[8 x 4] . Y[4 x 8]
+//     Gpart += A^T U         (d x 8)        D[8 cols x 8 lambda] += A_tile^T[8 x 4] . U[4 x 8]
+//
+// i.e. the batched form of iterative_solvers.py:173-175 (r = A y - b; grad = A^T r), each column
+// with its own penalty.  Arithmetic intensity 32 flop / 8 B: the kernel sits between the HBM and
+// the DMMA roofline (76 % tensor-pipe duty at the HBM rate for d = 4096).
+//
+// Decomposition.  Y (d x 8) and the accumulators (d x 8) do not fit one CTA's registers at d = 4096,
+// so a thread-block CLUSTER of 4 CTAs shares a row block: CTA q owns the column quarter q (Y and
+// accumulator slices live in registers: 32 + 32 doubles per lane), streams the quarter-rows of its
+// 8-row tiles through its own cp.async.bulk ring (one bulk copy per row, padded pitch: conflict-free
+// DMMA fragment loads), and the partial products U_q (8 x 8) are summed across the cluster through
+// distributed shared memory in rank order -- one split-phase cluster barrier per tile, overlapped with
+// the first contraction of the NEXT tile (software pipeline: arrive(t+1) ... wait(t+1) one tile later).
+// Every sum has a fixed order: results are bit-reproducible.
+//
+//   mrhs_stream_kernel<CW>   one pass: per-cluster partial gradients + per-column residual norms
+//   mrhs_update_kernel       sum of the cluster partials (fixed order), (+a2 y), soft threshold with
+//                            the column's penalty, Nesterov step (same roundings as pg_logic.cuh)
+//   mrhs_obj_kernel          objective of every column from a norms-only pass
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "fos_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int MR_CLUSTER = 4;    // CTAs per row block (column quarters)
+constexpr int MR_TILE = 8;       // rows per tile (the M of the first contraction, the K of the second)
+constexpr int MR_NB = 8;         // penalties per pass (the N of both contractions)
+constexpr int MR_PAD = 32;       // bytes added to the shared row pitch (8 words: conflict-free fragments)
+constexpr int MR_MAXST = 8;
+
+__device__ __forceinline__ uint32_t mr_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mr_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mr_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MR_DONE;\n\t"
+        "bra MR_WAIT;\n\t"
+        "MR_DONE:\n\t"
+        "}" ::"r"(mr_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mr_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            mr_smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(mr_smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void mr_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mr_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mr_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+struct MrhsArgs {
+    const double* A;        // n x lda row-major fp64
+    const double* b;        // n
+    const double* Y;        // [8][ldv] the batch's points (row l = penalty l)
+    double* part;           // [n_clusters][8][ldv] per-cluster partial gradients
+    double* norms;          // [n_clusters][8] per-cluster sum_i r_il^2
+    const long long* row_lo;  // [n_clusters + 1], multiples of 8 except the last entry (= n)
+    int d, lda, ldv;
+    int grad;               // 1: gradient + norms, 0: norms only (objective pass)
+    int nstage, stage_bytes, pitch;  // ring geometry (pitch in bytes)
+};
+
+struct MrhsSmem {
+    uint64_t full[MR_MAXST];
+    double red[2][8][64];             // [parity][warp][row*8 + lambda] warp partials of U
+    double clu[2][MR_CLUSTER][64];    // [parity][source CTA][row*8 + lambda] CTA partials (written through DSMEM)
+    double bt[2][MR_TILE];            // b of the tile
+};
+
+// CW: columns per warp (d / 32): 128 for d = 4096, 64 for d = 2048, 32 for d = 1024
+template <int CW>
+__global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(256, 1) mrhs_stream_kernel(const MrhsArgs a) {
+    constexpr int KS = CW / 4;   // k-steps of the first contraction per warp
+    constexpr int MB = CW / 8;   // column blocks of the second contraction per warp
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(16) MrhsSmem sm;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fk = lane & 3, fc = lane >> 2;
+    const int q = static_cast<int>(cluster.block_rank());      // column quarter
+    const int cl = blockIdx.x / MR_CLUSTER;                    // row block
+    const long long lo = a.row_lo[cl], hi = a.row_lo[cl + 1];
+    const int ntile = static_cast<int>((hi - lo + MR_TILE - 1) / MR_TILE);
+    const int dq = a.d / MR_CLUSTER;
+    const int col0 = q * dq + warp * CW;                       // first column of this warp
+    const uint32_t row_bytes = static_cast<uint32_t>(dq) * 8u;
+
+    uint64_t pol = 0;
+    auto fill = [&](int t) {   // thread 0: request tile t into slot t % nstage
+        const int slot = t % a.nstage;
+        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+        mr_mbar_expect_tx(&sm.full[slot], static_cast<uint32_t>(rows) * row_bytes);
+        for (int r = 0; r < rows; ++r)
+            mr_bulk_g2s(ring + static_cast<size_t>(slot) * a.stage_bytes + static_cast<size_t>(r) * a.pitch,
+                        a.A + (r0 + r) * a.lda + q * dq, row_bytes, &sm.full[slot], pol);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < a.nstage; ++s) mr_mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        for (int t = 0; t < a.nstage && t < ntile; ++t) fill(t);
+    }
+
+    // Y fragments of this warp's columns: B[k = col][n = lambda] -> lane holds Y[lambda fc][col k0 + fk]
+    double yb[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) yb[k] = a.Y[static_cast<size_t>(fc) * a.ldv + col0 + 4 * k + fk];
+    double acc[MB][2];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) acc[m][0] = acc[m][1] = 0.0;
+    double nrm0 = 0.0, nrm1 = 0.0;   // (cluster rank 0, warp 0): sum of squares of R[fk][fc] and R[fk+4][fc]
+
+    __syncthreads();
+    cluster.sync();   // every CTA's barriers and shared arrays exist before anyone writes into a peer
+
+    // first contraction of tile t: partial U of this warp's columns -> sm.red[t & 1][warp]
+    auto contract1 = [&](int t) {
+        const int slot = t % a.nstage;
+        mr_mbar_wait(&sm.full[slot], static_cast<uint32_t>(t / a.nstage) & 1u);
+        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+        const unsigned char* base = ring + static_cast<size_t>(slot) * a.stage_bytes;
+        const double* arow = reinterpret_cast<const double*>(base + static_cast<size_t>(fc) * a.pitch) + warp * CW + fk;
+        double u[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u[c][0] = u[c][1] = 0.0;
+        const bool live = fc < rows;   // rows past the end of the block: the slot holds stale bytes there
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const double av = live ? arow[4 * k] : 0.0;
+            mr_dmma(u[k & 3][0], u[k & 3][1], av, yb[k]);
+        }
+        const double u0 = (u[0][0] + u[1][0]) + (u[2][0] + u[3][0]);
+        const double u1 = (u[0][1] + u[1][1]) + (u[2][1] + u[3][1]);
+        *reinterpret_cast<double2*>(&sm.red[t & 1][warp][fc * 8 + 2 * fk]) = make_double2(u0, u1);
+        if (warp == 0 && lane < MR_TILE) sm.bt[t & 1][lane] = (lane < rows) ? a.b[r0 + lane] : 0.0;
+    };
+    // CTA partial of tile t (ordered sum over the warps) into every cluster CTA, then arrive
+    auto publish = [&](int t) {
+        if (tid < 64) {
+            double v = sm.red[t & 1][0][tid];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) v += sm.red[t & 1][w][tid];
+#pragma unroll
+            for (int r = 0; r < MR_CLUSTER; ++r) *cluster.map_shared_rank(&sm.clu[t & 1][q][tid], r) = v;
+        }
+        mr_cluster_arrive();
+    };
+    // second contraction of tile t: R = sum_q U_q - b (rank order), accumulators += A_tile^T R
+    auto contract2 = [&](int t) {
+        mr_cluster_wait();
+        const int slot = t % a.nstage;
+        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+        double rlo = 0.0, rhi = 0.0;
+        {
+            const int i0 = fk * 8 + fc, i1 = (fk + 4) * 8 + fc;
+            double s0 = sm.clu[t & 1][0][i0], s1 = sm.clu[t & 1][0][i1];
+#pragma unroll
+            for (int r = 1; r < MR_CLUSTER; ++r) {
+                s0 += sm.clu[t & 1][r][i0];
+                s1 += sm.clu[t & 1][r][i1];
+            }
+            rlo = (fk < rows) ? s0 - sm.bt[t & 1][fk] : 0.0;
+            rhi = (fk + 4 < rows) ? s1 - sm.bt[t & 1][fk + 4] : 0.0;
+        }
+        nrm0 = fma(rlo, rlo, nrm0);
+        nrm1 = fma(rhi, rhi, nrm1);
+        if (a.grad) {
+            const unsigned char* base = ring + static_cast<size_t>(slot) * a.stage_bytes;
+            const double* alo = reinterpret_cast<const double*>(base + static_cast<size_t>(fk) * a.pitch) + warp * CW + fc;
+            const double* ahi = reinterpret_cast<const double*>(base + static_cast<size_t>(fk + 4) * a.pitch) + warp * CW + fc;
+            const bool live_lo = fk < rows, live_hi = fk + 4 < rows;
+#pragma unroll
+            for (int m = 0; m < MB; ++m) {
+                const double a_lo = live_lo ? alo[8 * m] : 0.0;
+                const double a_hi = live_hi ? ahi[8 * m] : 0.0;
+                mr_dmma(acc[m][0], acc[m][1], a_lo, rlo);
+                mr_dmma(acc[m][0], acc[m][1], a_hi, rhi);
+            }
+        }
+    };
+
+    // ---- software pipeline: contract1(t+1) runs between arrive(t) ... wait(t)
+    if (ntile > 0) {
+        contract1(0);
+        __syncthreads();
+        publish(0);
+    } else {
+        mr_cluster_arrive();   // keep the cluster barrier phases aligned with the peers (all blocks have the same ntile)
+    }
+    for (int t = 0; t < ntile; ++t) {
+        const bool has_next = t + 1 < ntile;
+        if (has_next) contract1(t + 1);
+        contract2(t);
+        __syncthreads();   // everybody is done with slot t % nstage and with red[(t+1)&1]
+        if (tid == 0 && t + a.nstage < ntile) fill(t + a.nstage);
+        if (has_next) publish(t + 1);
+    }
+    if (ntile == 0) mr_cluster_wait();
+
+    // ---- results: C fragment -> G[col m0 + fc][lambda 2 fk + {0,1}]
+    if (a.grad) {
+        double* out = a.part + static_cast<size_t>(cl) * MR_NB * a.ldv;
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+            const int col = col0 + 8 * m + fc;
+            out[static_cast<size_t>(2 * fk) * a.ldv + col] = acc[m][0];
+            out[static_cast<size_t>(2 * fk + 1) * a.ldv + col] = acc[m][1];
+        }
+    }
+    if (q == 0 && warp == 0) {
+        // lanes with the same fc hold rows fk and fk+4 of column lambda = fc: sum over fk (lane bits 0,1)
+        double v = nrm0 + nrm1;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (fk == 0) a.norms[static_cast<size_t>(cl) * MR_NB + fc] = v;
+    }
+    cluster.sync();   // nobody exits while a peer may still write into its shared memory
+}
+
+struct MrhsUpdateArgs {
+    const double* part;    // [ncl][8][ldv]
+    const double* Yin;     // [8][ldv]
+    double* Yout;          // [8][ldv]
+    double* X;             // [8][ldv] in: x_k, out: x_{k+1}
+    const double* alpha1;  // [8]
+    double alpha2, tau, beta;
+    int d, ldv, ncl;
+    double* step_part;     // [gridDim.x][8] partial sums of (x+ - x)^2 (nullable)
+};
+
+// one thread per (column, penalty); the cluster partials are summed in cluster order
+__global__ void __launch_bounds__(256) mrhs_update_kernel(const MrhsUpdateArgs u) {
+    __shared__ double red[8][8];
+    const int l = threadIdx.x >> 5;          // penalty = warp
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 32 + lane;
+    double dx2 = 0.0;
+    if (col < u.d) {
+        const size_t idx = static_cast<size_t>(l) * u.ldv + col;
+        double g = 0.0;
+        for (int c = 0; c < u.ncl; ++c) g += u.part[(static_cast<size_t>(c) * MR_NB + l) * u.ldv + col];
+        const double y = u.Yin[idx], xk = u.X[idx];
+        if (u.alpha2 > 0.0) g = __dadd_rn(g, __dmul_rn(u.alpha2, y));
+        double v = __dsub_rn(y, __dmul_rn(u.tau, g));
+        const double a1 = u.alpha1[l];
+        if (a1 > 0.0) v = fos_soft_threshold(v, __dmul_rn(u.tau, a1));
+        u.X[idx] = v;
+        u.Yout[idx] = __dadd_rn(v, __dmul_rn(u.beta, __dsub_rn(v, xk)));
+        const double dx = v - xk;
+        dx2 = dx * dx;
+    }
+    if (u.step_part != nullptr) {
+        dx2 = fos_warp_sum(dx2);
+        if (lane == 0) u.step_part[static_cast<size_t>(blockIdx.x) * MR_NB + l] = dx2;
+    }
+    (void)red;
+}
+
+// objective of the 8 columns of X: 0.5 sum_c norms[c][l] (+0.5 a2 |x|^2) (+a1[l] |x|_1); one warp per penalty
+__global__ void __launch_bounds__(256) mrhs_obj_kernel(const double* __restrict__ norms, int ncl, const double* __restrict__ X,
+                                                       int d, int ldv, const double* __restrict__ alpha1, double alpha2,
+                                                       double* __restrict__ obj) {
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double l1 = 0.0, l2 = 0.0;
+    for (int c = lane; c < d; c += 32) {
+        const double x = X[static_cast<size_t>(l) * ldv + c];
+        l1 += fabs(x);
+        l2 = fma(x, x, l2);
+    }
+    l1 = fos_warp_sum(l1);
+    l2 = fos_warp_sum(l2);
+    if (lane == 0) {
+        double s = 0.0;
+        for (int c = 0; c < ncl; ++c) s += norms[static_cast<size_t>(c) * MR_NB + l];
+        double v = 0.5 * s;
+        if (alpha2 > 0.0) v += 0.5 * alpha2 * l2;
+        if (alpha1[l] > 0.0) v += alpha1[l] * l1;
+        obj[l] = v;
+    }
+}
+
+__global__ void mrhs_step_finish_kernel(const double* __restrict__ part, int nblk, int n_live, double* __restrict__ out) {
+    // max over the live penalties of ||x+ - x||_2 (blocks summed in order); 8 threads
+    __shared__ double red[8];
+    const int l = threadIdx.x;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += part[static_cast<size_t>(b) * MR_NB + l];
+    red[l] = (l < n_live) ? sqrt(s) : 0.0;
+    __syncthreads();
+    if (l == 0) {
+        double m = 0.0;
+        for (int i = 0; i < 8; ++i) m = fmax(m, red[i]);
+        out[0] = fmax(out[0], m);
+    }
+}
+
+const void* mrhs_kernel_for(int cw) {
+    switch (cw) {
+        case 128: return reinterpret_cast<const void*>(&mrhs_stream_kernel<128>);
+        case 64: return reinterpret_cast<const void*>(&mrhs_stream_kernel<64>);
+        case 32: return reinterpret_cast<const void*>(&mrhs_stream_kernel<32>);
+        default: return nullptr;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side: fos_mrhs_fista (include/fos.h)
+// ------------------------------------------------------------------------------------------
+extern "C" int fos_mrhs_fista(fos_design* h, const fos_path_params* pp, fos_path_result* pr) {
+    FOS_REQUIRE(h && pp && pr, "null pointer argument");
+    FOS_REQUIRE(pp->n_lambda >= 1 && pp->alphas1 != nullptr, "at least one penalty is required");
+    FOS_REQUIRE(pp->step > 0.0 && pp->max_iter >= 0, "step must be positive, max_iter >= 0");
+    FOS_REQUIRE(h->world == 1, "the streaming multi-RHS mode runs on one GPU (row-sharded designs: use the Gram mode)");
+    if (h->dtype != FOS_F64 || h->lda != h->d || h->d % 1024 != 0 || h->d > 4096 || (h->d / 32 != 32 && h->d / 32 != 64 && h->d / 32 != 128)) {
+        fos_set_error("streaming multi-RHS mode needs a dense float64 design with d in {1024, 2048, 4096} (got d = %d)", h->d);
+        return FOS_ERR_UNSUPPORTED;
+    }
+    FOS_CUDA(cudaSetDevice(h->device));
+    const int d = h->d, ldv = h->ldv, CW = d / 32;
+    const int ncl = std::max(1, h->sm_count / MR_CLUSTER);
+    const int n_lambda = pp->n_lambda;
+    const int nbatch = (n_lambda + MR_NB - 1) / MR_NB;
+    const int Lpad = nbatch * MR_NB;
+    const void* fn = mrhs_kernel_for(CW);
+    const int dq = d / MR_CLUSTER;
+    const int pitch = dq * 8 + MR_PAD;
+    const int stage_bytes = (MR_TILE * pitch + 127) & ~127;
+    const int nstage = std::min(MR_MAXST, (200 * 1024) / stage_bytes);
+    FOS_REQUIRE(nstage >= 2, "row too wide for the multi-RHS ring");
+    FOS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, nstage * stage_bytes));
+
+    // row blocks: multiples of MR_TILE rows, the last cluster takes the tail
+    std::vector<long long> row_lo(ncl + 1);
+    for (int c = 0; c <= ncl; ++c) row_lo[c] = std::min<long long>(h->n, ((h->n * c / ncl) + MR_TILE - 1) / MR_TILE * MR_TILE);
+    row_lo[0] = 0;
+    row_lo[ncl] = h->n;
+
+    const size_t vec = static_cast<size_t>(Lpad) * ldv * sizeof(double);
+    double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *norms = nullptr, *obj = nullptr,
+           *spart = nullptr, *smax = nullptr;
+    long long* rl = nullptr;
+    double* smax_host = nullptr;
+    const int ublk = (d + 31) / 32;
+    auto cleanup = [&]() {
+        for (void* p : {static_cast<void*>(Y0), static_cast<void*>(Y1), static_cast<void*>(X), static_cast<void*>(a1),
+                        static_cast<void*>(part), static_cast<void*>(norms), static_cast<void*>(obj),
+                        static_cast<void*>(spart), static_cast<void*>(smax), static_cast<void*>(rl), static_cast<void*>(smax_host)})
+            fos_pool_free(p);
+    };
+    cudaStream_t s = h->stream;
+    auto body = [&]() -> int {
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&Y0), vec));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&Y1), vec));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&X), vec));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&a1), Lpad * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&part), static_cast<size_t>(ncl) * MR_NB * ldv * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&norms), static_cast<size_t>(ncl) * MR_NB * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&obj), Lpad * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&spart), static_cast<size_t>(ublk) * MR_NB * sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&smax), sizeof(double)));
+        FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&rl), (ncl + 1) * sizeof(long long)));
+        FOS_CUDA(fos_pool_malloc_host(reinterpret_cast<void**>(&smax_host), sizeof(double)));
+        FOS_CUDA(cudaMemsetAsync(Y0, 0, vec, s));
+        FOS_CUDA(cudaMemsetAsync(Y1, 0, vec, s));
+        FOS_CUDA(cudaMemsetAsync(X, 0, vec, s));
+        FOS_CUDA(cudaMemsetAsync(a1, 0, Lpad * sizeof(double), s));
+        FOS_CUDA(cudaMemcpyAsync(a1, pp->alphas1, n_lambda * sizeof(double), cudaMemcpyHostToDevice, s));
+        FOS_CUDA(cudaMemcpyAsync(rl, row_lo.data(), (ncl + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+        if (pp->X0) {
+            FOS_CUDA(cudaMemcpy2DAsync(X, ldv * sizeof(double), pp->X0, d * sizeof(double), d * sizeof(double), n_lambda,
+                                       cudaMemcpyHostToDevice, s));
+            FOS_CUDA(cudaMemcpyAsync(Y0, X, vec, cudaMemcpyDeviceToDevice, s));
+        }
+        MrhsArgs ma{};
+        ma.A = static_cast<const double*>(h->A);
+        ma.b = h->b;
+        ma.row_lo = rl;
+        ma.d = d;
+        ma.lda = h->lda;
+        ma.ldv = ldv;
+        ma.nstage = nstage;
+        ma.stage_bytes = stage_bytes;
+        ma.pitch = pitch;
+        ma.part = part;
+        ma.norms = norms;
+        auto launch_pass = [&](const double* Yb, int grad) -> int {
+            ma.Y = Yb;
+            ma.grad = grad;
+            void* params[1] = {&ma};
+            FOS_CUDA(fos_launch_ex(fn, dim3(ncl * MR_CLUSTER), dim3(256), static_cast<size_t>(nstage) * stage_bytes, s, params,
+                                   false, 0));
+            h->launches++;
+            return FOS_OK;
+        };
+        const long long launches0 = h->launches;
+        FOS_CUDA(cudaEventRecord(h->ev0, s));
+        double t_prev = 1.0;
+        double* Yin = Y0;
+        double* Yout = Y1;
+        int it = 0;
+        double last_max = 0.0;
+        const int check = std::max(1, pp->check_every);
+        for (; it < pp->max_iter; ++it) {
+            const double t_cur = 0.5 * (1.0 + sqrt(1.0 + 4.0 * (t_prev * t_prev)));
+            const double beta = (t_prev - 1.0) / t_cur;
+            const bool chk = pp->tol > 0.0 && ((it + 1) % check == 0);
+            if (chk) FOS_CUDA(cudaMemsetAsync(smax, 0, sizeof(double), s));
+            for (int bt = 0; bt < nbatch; ++bt) {
+                const size_t off = static_cast<size_t>(bt) * MR_NB * ldv;
+                FOS_TRY(launch_pass(Yin + off, 1));
+                MrhsUpdateArgs ua{};
+                ua.part = part;
+                ua.Yin = Yin + off;
+                ua.Yout = Yout + off;
+                ua.X = X + off;
+                ua.alpha1 = a1 + bt * MR_NB;
+                ua.alpha2 = pp->alpha2;
+                ua.tau = pp->step;
+                ua.beta = beta;
+                ua.d = d;
+                ua.ldv = ldv;
+                ua.ncl = ncl;
+                ua.step_part = chk ? spart : nullptr;
+                mrhs_update_kernel<<<dim3(ublk), dim3(256), 0, s>>>(ua);
+                h->launches++;
+                if (chk) {
+                    mrhs_step_finish_kernel<<<1, 8, 0, s>>>(spart, ublk, std::min(MR_NB, n_lambda - bt * MR_NB), smax);
+                    h->launches++;
+                }
+            }
+            FOS_CUDA(cudaGetLastError());
+            std::swap(Yin, Yout);
+            t_prev = t_cur;
+            if (chk) {
+                FOS_CUDA(cudaMemcpyAsync(smax_host, smax, sizeof(double), cudaMemcpyDeviceToHost, s));
+                FOS_CUDA(cudaStreamSynchronize(s));
+                last_max = *smax_host;
+                if (last_max < pp->tol) {
+                    ++it;
+                    break;
+                }
+            }
+        }
+        // objectives of the final iterates: one norms-only pass per batch
+        for (int bt = 0; bt < nbatch; ++bt) {
+            const size_t off = static_cast<size_t>(bt) * MR_NB * ldv;
+            FOS_TRY(launch_pass(X + off, 0));
+            mrhs_obj_kernel<<<1, 256, 0, s>>>(norms, ncl, X + off, d, ldv, a1 + bt * MR_NB, pp->alpha2, obj + bt * MR_NB);
+            h->launches++;
+        }
+        FOS_CUDA(cudaGetLastError());
+        FOS_CUDA(cudaEventRecord(h->ev1, s));
+        FOS_CUDA(cudaStreamSynchronize(s));
+        if (pr->X)
+            FOS_CUDA(cudaMemcpy2D(pr->X, d * sizeof(double), X, ldv * sizeof(double), d * sizeof(double), n_lambda,
+                                  cudaMemcpyDeviceToHost));
+        if (pr->obj) FOS_CUDA(cudaMemcpy(pr->obj, obj, n_lambda * sizeof(double), cudaMemcpyDeviceToHost));
+        FOS_CUDA(cudaEventElapsedTime(&pr->loop_ms, h->ev0, h->ev1));
+        pr->kernel_launches = h->launches - launches0;
+        pr->n_iters = it;
+        pr->last_max_step = last_max;
+        pr->tile_rows = MR_TILE;
+        return FOS_OK;
+    };
+    const int st = body();
+    if (st != FOS_OK) cudaStreamSynchronize(s);
+    cleanup();
+    return st;
+}

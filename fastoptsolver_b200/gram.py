@@ -156,6 +156,40 @@ def fista_path(A, b, alphas1, alpha2=0.0, t_init_factor=1.0, max_iter=500, L=Non
     return X, info
 
 
+def fista_path_stream(A, b, alphas1, alpha2=0.0, t_init_factor=1.0, max_iter=500, L=None, tol=0.0, check_every=10,
+                      X0=None):
+    """``fista_path`` without the Gram matrix: every iteration streams A once per batch of 8 penalties
+    and forms A Y - b 1^T and A^T(.) on the fp64 tensor cores inside one kernel (include/fos.h:
+    fos_mrhs_fista).  For designs where d^2 doubles do not fit, or n is not >> d so that building G
+    costs more than the iterations it saves.  Same arguments and return value as ``fista_path``; column
+    l reproduces ``fista(A, b, ..., alphas1[l], alpha2, backtracking=False)`` of the reference
+    (iterative_solvers.py:132-245)."""
+    des = as_design(A, b)
+    alphas1 = np.ascontiguousarray(alphas1, dtype=np.float64).reshape(-1)
+    if L is None:
+        L = S.estimate_lipschitz(des)
+        if alpha2 > 0:
+            L += alpha2
+    d = des.shape[1]
+    X = np.empty((alphas1.size, d))
+    obj = np.empty(alphas1.size)
+    p = _lib.PathParams(alphas1=alphas1.ctypes.data_as(_lib.c_double_p), n_lambda=alphas1.size, alpha2=float(alpha2),
+                        step=float(t_init_factor / L), max_iter=int(max_iter), tol=float(tol),
+                        check_every=int(check_every))
+    if X0 is not None:
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        if X0.shape != X.shape:
+            raise ValueError(f"X0 must have shape {X.shape}, got {X0.shape}")
+        p.X0 = X0.ctypes.data_as(_lib.c_double_p)
+    r = _lib.PathResult(X=X.ctypes.data_as(_lib.c_double_p), obj=obj.ctypes.data_as(_lib.c_double_p))
+    _lib.check(_lib.load().fos_mrhs_fista(des.handle, C.byref(p), C.byref(r)))
+    info = {"obj": obj, "L": float(L), "loop_ms": r.loop_ms, "launches": r.kernel_launches, "iters": r.n_iters,
+            "last_max_step": r.last_max_step, "batches": (alphas1.size + 7) // 8}
+    if des is not A:
+        des.close()
+    return X, info
+
+
 def fista_path_warm(A, b, alphas1, alpha2=0.0, chunk=32, tol=1e-8, max_iter=5000, check_every=10, L=None, gram=None):
     """The path solved to tolerance in decreasing-penalty chunks, each chunk warm-started from the
     previous chunk's last (smallest-penalty) solution -- the sequential-with-warm-start strategy,

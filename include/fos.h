@@ -301,6 +301,16 @@ typedef struct fos_path_result {
 } fos_path_result;
 int fos_gram_path_fista(fos_gram* g, const fos_path_params* p, fos_path_result* r);
 
+/* ---- streaming multi-RHS mode: the same batched fixed-step FISTA WITHOUT the Gram matrix ----------
+ * For designs where d^2 does not fit or n is not >> d.  Every iteration streams A once per batch of 8
+ * penalties; U = A Y - b 1^T and A^T U (iterative_solvers.py:173-175, batched over the columns) both
+ * run on the fp64 tensor pipe inside one kernel, a cluster of 4 CTAs sharing a row block (csrc/
+ * mrhs_kernels.cu).  Column l reproduces fista(A, b, ..., alpha1 = alphas1[l], alpha2, backtracking =
+ * False) (iterative_solvers.py:132-245).  r->obj = 0.5 |A x - b|^2 (+0.5 alpha2 |x|^2) (+alpha1 |x|_1),
+ * from one norms-only pass per batch.  Dense float64 designs with d in {1024, 2048, 4096}, one GPU;
+ * FOS_ERR_UNSUPPORTED otherwise. */
+int fos_mrhs_fista(fos_design* h, const fos_path_params* p, fos_path_result* r);
+
 #ifdef __cplusplus
 }
 #endif
