@@ -90,6 +90,8 @@ SIGNATURES = {
     "fos_device_info": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "fos_design_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                     C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "fos_design_create_begin": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fos_design_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "fos_design_create_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                            C.c_int, C.POINTER(C.c_void_p)]),
     "fos_design_create_synthetic": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.c_double, C.c_double,

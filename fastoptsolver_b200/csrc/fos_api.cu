@@ -258,6 +258,7 @@ static int design_common_init(fos_design* h, long long n, long long d, int dtype
         const char* e = getenv("FOS_NO_PDL");
         h->pdl = !(e && e[0] == '1');
     }
+    if (h->life_mu == nullptr) h->life_mu = new std::mutex();
     FOS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     FOS_CUDA(cudaEventCreate(&h->ev0));
     FOS_CUDA(cudaEventCreate(&h->ev1));
@@ -484,6 +485,7 @@ static void design_free(fos_design* h) {
         cudaFree(h->window);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
+    delete h->life_mu;
     delete h;
 }
 
@@ -799,14 +801,28 @@ static int upload_dense(fos_design* h, const void* A, HostStager& stager, bool w
     return st;
 }
 
-extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
-                                 int64_t row_stride, int64_t col_stride, int device, fos_design** out) {
-    FOS_REQUIRE(A && b && out, "null pointer argument");
+// Two-step creation: fos_design_create_begin allocates everything (matrix block, workspaces, control
+// block -- recycled blocks in the steady state, so this takes well under a millisecond) and returns a
+// handle whose matrix is still undefined; fos_design_upload then copies the host arrays.  Row-sharded
+// callers run the upload on a side thread while the main thread wires the exchange windows of the same
+// handle (socket hand-off + two all-gathers, ~0.1 s that used to follow the copy).
+extern "C" int fos_design_create_begin(int64_t n, int64_t d, int dtype, int device, fos_design** out) {
+    FOS_REQUIRE(out, "null pointer argument");
     fos_design* h = new fos_design();
-    const auto t0 = std::chrono::steady_clock::now();
     FOS_TRY_FREE(h, design_common_init(h, n, d, dtype, device));
-    const auto t1 = std::chrono::steady_clock::now();
     FOS_TRY_FREE(h, alloc_matrix(h));
+    FOS_TRY_FREE(h, design_alloc_work(h));
+    *out = h;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_upload(fos_design* h, const void* A, const double* b, int64_t row_stride, int64_t col_stride) {
+    FOS_REQUIRE(h && A && b, "null pointer argument");
+    FOS_REQUIRE(h->owns_A && h->owns_b, "this design borrows its arrays; it cannot be uploaded into");
+    FOS_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n, d = h->d;
+    const int dtype = h->dtype;
+    const int device = h->device;
     const auto t2 = std::chrono::steady_clock::now();
     const size_t es = elem_size(dtype);
     HostStager stager;
@@ -866,18 +882,35 @@ extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int6
         FOS_CUDA(cudaStreamSynchronize(h->stream));
         return FOS_OK;
     };
-    const int st_body = body();
-    stager.drain();  // no copy may be in flight when the matrix is freed on the error path
-    FOS_TRY_FREE(h, st_body);
-    const auto t3 = std::chrono::steady_clock::now();
-    FOS_TRY_FREE(h, design_alloc_work(h));
-    if (getenv("FOS_UPLOAD_DEBUG")) {
-        const auto t4 = std::chrono::steady_clock::now();
-        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[fos] design_create %lld x %lld: init %.1f ms, cudaMalloc %.1f ms, copy %.1f ms (device %.1f), "
-                        "workspaces %.1f ms\n", static_cast<long long>(n), static_cast<long long>(d), ms(t0, t1), ms(t1, t2),
-                ms(t2, t3), h->up_copy_ms, ms(t3, t4));
+    {
+        std::lock_guard<std::mutex> lock(*h->life_mu);
+        h->uploading = true;
     }
+    const int st_body = body();
+    stager.drain();  // no copy may be in flight when the caller frees the design on the error path
+    bool pending;
+    {
+        std::lock_guard<std::mutex> lock(*h->life_mu);
+        h->uploading = false;
+        pending = h->balance_pending;
+        h->balance_pending = false;
+    }
+    if (st_body != FOS_OK) return st_body;
+    if (pending) FOS_TRY(fos_balance_rows(h));
+    if (getenv("FOS_UPLOAD_DEBUG")) {
+        const auto t3 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fos] design_upload %lld x %lld: copy %.1f ms (device %.1f)\n", static_cast<long long>(n),
+                static_cast<long long>(d), std::chrono::duration<double, std::milli>(t3 - t2).count(), h->up_copy_ms);
+    }
+    return FOS_OK;
+}
+
+extern "C" int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
+                                 int64_t row_stride, int64_t col_stride, int device, fos_design** out) {
+    FOS_REQUIRE(A && b && out, "null pointer argument");
+    fos_design* h = nullptr;
+    FOS_TRY(fos_design_create_begin(n, d, dtype, device, &h));
+    FOS_TRY_FREE(h, fos_design_upload(h, A, b, row_stride, col_stride));
     *out = h;
     return FOS_OK;
 }
@@ -1573,7 +1606,16 @@ extern "C" int fos_comm_attach(fos_design* h, const void* ipc_handles, int world
 
 int fos_comm_after_attach(fos_design* h) {
     const char* e = getenv("FOS_BALANCE");
-    if (h->world >= 4 && !(e && e[0] == '0') && !h->balanced) FOS_TRY(fos_balance_rows(h));
+    if (h->world >= 4 && !(e && e[0] == '0') && !h->balanced) {
+        {
+            std::lock_guard<std::mutex> lock(*h->life_mu);
+            if (h->uploading) {  // calibrate once the copy is done (fos_design_upload's last step)
+                h->balance_pending = true;
+                return FOS_OK;
+            }
+        }
+        FOS_TRY(fos_balance_rows(h));
+    }
     return FOS_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -201,7 +203,7 @@ struct fos_design {
     FosCtrl* ctrl_host = nullptr;  // pinned mirror
     double* vec_host = nullptr;    // pinned staging, 2*ldv + 8 doubles
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    long long launches = 0;
+    std::atomic<long long> launches{0};  // also bumped by the upload thread of a two-step creation
     // multi-GPU
     int world = 1, rank = 0;
     void* window = nullptr;        // this rank's exchange window (cudaMalloc, IPC-exported)
@@ -226,6 +228,11 @@ struct fos_design {
     int* sm_slot = nullptr;                   // device: SM id -> slot, set when the partition is SM-indexed;
                                               // followed by n_parts claim words (GradArgs::slot_claim)
     bool balanced = false;
+    // two-step creation: the exchange windows may be attached (another host thread) while the upload is
+    // still running; the rate-weighted row partition must not be calibrated under a PCIe copy, so it is
+    // deferred to the end of the upload
+    std::mutex* life_mu = nullptr;
+    bool uploading = false, balance_pending = false;
     bool pdl = true;  // launch passes with programmatic dependent launch (FOS_NO_PDL=1 disables)
     void* arena = nullptr;         // grow-only device workspace of the per-solve arrays (fos_arena_reserve)
     size_t arena_bytes = 0;

@@ -26,6 +26,8 @@
 //   mrhs_obj_kernel          objective of every column from a norms-only pass
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -86,20 +88,46 @@ struct MrhsArgs {
     int d, lda, ldv;
     int grad;               // 1: gradient + norms, 0: norms only (objective pass)
     int nstage, stage_bytes, pitch;  // ring geometry (pitch in bytes)
+    unsigned long long* prof;        // debug (nullable): clock64 cycles of block 0 / thread 0 per phase
 };
+
+constexpr int MR_UBUF = 4;       // buffers of the cluster exchange (a CTA may run up to 3 tiles ahead of a slow peer warp)
+constexpr int MR_THREADS = 288;  // 8 consumer warps + 1 producer warp
 
 struct MrhsSmem {
-    uint64_t full[MR_MAXST];
+    uint64_t full[MR_MAXST];          // tile landed (bulk-copy bytes)
+    uint64_t empty[MR_MAXST];         // all 8 consumer warps are done with the slot
+    uint64_t redbar[2];               // all 8 warps stored their partial U of a tile
+    uint64_t ubar[MR_UBUF];           // the CTA partials of all 4 cluster CTAs arrived (st.async bytes)
     double red[2][8][64];             // [parity][warp][row*8 + lambda] warp partials of U
-    double clu[2][MR_CLUSTER][64];    // [parity][source CTA][row*8 + lambda] CTA partials (written through DSMEM)
-    double bt[2][MR_TILE];            // b of the tile
+    double clu[MR_UBUF][MR_CLUSTER][64];  // [buffer][source CTA][row*8 + lambda], written by st.async from the peers
 };
 
-// CW: columns per warp (d / 32): 128 for d = 4096, 64 for d = 2048, 32 for d = 1024
+__device__ __forceinline__ void mr_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mr_mapa(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+// 8-byte store into a peer CTA's shared memory that also counts its bytes on the peer's mbarrier
+__device__ __forceinline__ void mr_st_async(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v),
+                 "r"(remote_bar)
+                 : "memory");
+}
+
+// CW: columns per warp (d / 32): 128 for d = 4096, 64 for d = 2048, 32 for d = 1024.
+// Control flow: no block-wide barrier inside the loop.  Warp 8 only moves data (waits for a free slot,
+// requests the next tile); warps 0-7 run   contract1(t+1) -> [warps 0,1: publish(t+1)] -> contract2(t)
+// and meet only through mbarriers: redbar (warp partials complete), ubar (the 4 CTA partials arrived
+// from the cluster, counted in bytes by st.async), empty (slot reusable).
 template <int CW>
-__global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(256, 1) mrhs_stream_kernel(const MrhsArgs a) {
+__global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS, 1) mrhs_stream_kernel(const MrhsArgs a) {
     constexpr int KS = CW / 4;   // k-steps of the first contraction per warp
     constexpr int MB = CW / 8;   // column blocks of the second contraction per warp
+    constexpr int NCH = 8;       // independent accumulation chains of the first contraction
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(16) MrhsSmem sm;
     cg::cluster_group cluster = cg::this_cluster();
@@ -110,140 +138,178 @@ __global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(256, 1) mrh
     const long long lo = a.row_lo[cl], hi = a.row_lo[cl + 1];
     const int ntile = static_cast<int>((hi - lo + MR_TILE - 1) / MR_TILE);
     const int dq = a.d / MR_CLUSTER;
-    const int col0 = q * dq + warp * CW;                       // first column of this warp
     const uint32_t row_bytes = static_cast<uint32_t>(dq) * 8u;
 
-    uint64_t pol = 0;
-    auto fill = [&](int t) {   // thread 0: request tile t into slot t % nstage
-        const int slot = t % a.nstage;
-        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
-        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
-        mr_mbar_expect_tx(&sm.full[slot], static_cast<uint32_t>(rows) * row_bytes);
-        for (int r = 0; r < rows; ++r)
-            mr_bulk_g2s(ring + static_cast<size_t>(slot) * a.stage_bytes + static_cast<size_t>(r) * a.pitch,
-                        a.A + (r0 + r) * a.lda + q * dq, row_bytes, &sm.full[slot], pol);
-    };
     if (tid == 0) {
-        for (int s = 0; s < a.nstage; ++s) mr_mbar_init(&sm.full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-        for (int t = 0; t < a.nstage && t < ntile; ++t) fill(t);
-    }
-
-    // Y fragments of this warp's columns: B[k = col][n = lambda] -> lane holds Y[lambda fc][col k0 + fk]
-    double yb[KS];
-#pragma unroll
-    for (int k = 0; k < KS; ++k) yb[k] = a.Y[static_cast<size_t>(fc) * a.ldv + col0 + 4 * k + fk];
-    double acc[MB][2];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) acc[m][0] = acc[m][1] = 0.0;
-    double nrm0 = 0.0, nrm1 = 0.0;   // (cluster rank 0, warp 0): sum of squares of R[fk][fc] and R[fk+4][fc]
-
-    __syncthreads();
-    cluster.sync();   // every CTA's barriers and shared arrays exist before anyone writes into a peer
-
-    // first contraction of tile t: partial U of this warp's columns -> sm.red[t & 1][warp]
-    auto contract1 = [&](int t) {
-        const int slot = t % a.nstage;
-        mr_mbar_wait(&sm.full[slot], static_cast<uint32_t>(t / a.nstage) & 1u);
-        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
-        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
-        const unsigned char* base = ring + static_cast<size_t>(slot) * a.stage_bytes;
-        const double* arow = reinterpret_cast<const double*>(base + static_cast<size_t>(fc) * a.pitch) + warp * CW + fk;
-        double u[4][2];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) u[c][0] = u[c][1] = 0.0;
-        const bool live = fc < rows;   // rows past the end of the block: the slot holds stale bytes there
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-            const double av = live ? arow[4 * k] : 0.0;
-            mr_dmma(u[k & 3][0], u[k & 3][1], av, yb[k]);
+        for (int s = 0; s < a.nstage; ++s) {
+            mr_mbar_init(&sm.full[s], 1);
+            mr_mbar_init(&sm.empty[s], 8);
         }
-        const double u0 = (u[0][0] + u[1][0]) + (u[2][0] + u[3][0]);
-        const double u1 = (u[0][1] + u[1][1]) + (u[2][1] + u[3][1]);
-        *reinterpret_cast<double2*>(&sm.red[t & 1][warp][fc * 8 + 2 * fk]) = make_double2(u0, u1);
-        if (warp == 0 && lane < MR_TILE) sm.bt[t & 1][lane] = (lane < rows) ? a.b[r0 + lane] : 0.0;
-    };
-    // CTA partial of tile t (ordered sum over the warps) into every cluster CTA, then arrive
-    auto publish = [&](int t) {
-        if (tid < 64) {
+        mr_mbar_init(&sm.redbar[0], 8);
+        mr_mbar_init(&sm.redbar[1], 8);
+        for (int u = 0; u < MR_UBUF; ++u) mr_mbar_init(&sm.ubar[u], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();   // every CTA's barriers exist before anyone signals a peer
+
+    if (warp == 8) {
+        // ===== producer warp: one lane requests tiles; a slot is refilled as soon as the 8 consumer warps released it
+        if (lane == 0) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            int slot = 0;
+            uint32_t round = 0;
+            for (int t = 0; t < ntile; ++t) {
+                if (round > 0) mr_mbar_wait(&sm.empty[slot], (round - 1u) & 1u);
+                const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+                const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+                mr_mbar_expect_tx(&sm.full[slot], static_cast<uint32_t>(rows) * row_bytes);
+                unsigned char* dst = ring + static_cast<size_t>(slot) * a.stage_bytes;
+                const double* src = a.A + r0 * a.lda + q * dq;
+                for (int r = 0; r < rows; ++r)
+                    mr_bulk_g2s(dst + static_cast<size_t>(r) * a.pitch, src + static_cast<size_t>(r) * a.lda, row_bytes,
+                                &sm.full[slot], pol);
+                if (++slot == a.nstage) {
+                    slot = 0;
+                    ++round;
+                }
+            }
+        }
+    } else {
+        // ===== consumer warps
+        const int col0 = q * dq + warp * CW;                       // first column of this warp
+        // Y fragments of this warp's columns: B[k = col][n = lambda] -> lane holds Y[lambda fc][col k0 + fk]
+        double yb[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) yb[k] = a.Y[static_cast<size_t>(fc) * a.ldv + col0 + 4 * k + fk];
+        double acc[MB][2];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) acc[m][0] = acc[m][1] = 0.0;
+        double nrm0 = 0.0, nrm1 = 0.0;   // sum of squares of R[fk][fc] and R[fk+4][fc]
+        const uint32_t clu_base = mr_smem_u32(&sm.clu[0][0][0]);
+        const uint32_t ubar_base = mr_smem_u32(&sm.ubar[0]);
+
+        double b_pref = 0.0; // (CTA 0, warps 0-1) b of the row this thread publishes next
+        if (q == 0 && warp < 2) {
+            const long long row = lo + (tid >> 3);
+            b_pref = (row < hi) ? __ldg(a.b + row) : 0.0;
+        }
+        int slot1 = 0;       // ring slot / round of the tile contract1 works on
+        uint32_t round1 = 0;
+        int slot2 = 0;       // ... and of the tile contract2 works on
+        // first contraction of tile t: partial U of this warp's columns -> sm.red[t & 1][warp]
+        auto contract1 = [&](int t) {
+            mr_mbar_wait(&sm.full[slot1], round1 & 1u);
+            const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+            const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+            const unsigned char* base = ring + static_cast<size_t>(slot1) * a.stage_bytes;
+            const double* arow = reinterpret_cast<const double*>(base + static_cast<size_t>(fc) * a.pitch) + warp * CW + fk;
+            double u[NCH][2];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) u[c][0] = u[c][1] = 0.0;
+            const bool live = fc < rows;   // rows past the end of the block: the slot holds stale bytes there
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const double av = live ? arow[4 * k] : 0.0;
+                mr_dmma(u[k % NCH][0], u[k % NCH][1], av, yb[k]);
+            }
+            const double u0 = ((u[0][0] + u[1][0]) + (u[2][0] + u[3][0])) + ((u[4][0] + u[5][0]) + (u[6][0] + u[7][0]));
+            const double u1 = ((u[0][1] + u[1][1]) + (u[2][1] + u[3][1])) + ((u[4][1] + u[5][1]) + (u[6][1] + u[7][1]));
+            *reinterpret_cast<double2*>(&sm.red[t & 1][warp][fc * 8 + 2 * fk]) = make_double2(u0, u1);
+            __syncwarp();
+            if (lane == 0) mr_mbar_arrive(&sm.redbar[t & 1]);
+            if (++slot1 == a.nstage) {
+                slot1 = 0;
+                ++round1;
+            }
+        };
+        // warps 0 and 1 (64 threads, one per entry of the 8 x 8 tile): ordered sum over the warps, CTA 0 folds in
+        // -b, then one st.async per cluster CTA (data + byte count on that CTA's barrier)
+        auto publish = [&](int t) {
+            mr_mbar_wait(&sm.redbar[t & 1], static_cast<uint32_t>(t >> 1) & 1u);
+            const int buf = t % MR_UBUF;
+            if (tid == 0) mr_mbar_expect_tx(&sm.ubar[buf], MR_CLUSTER * 64 * 8);
             double v = sm.red[t & 1][0][tid];
 #pragma unroll
             for (int w = 1; w < 8; ++w) v += sm.red[t & 1][w][tid];
-#pragma unroll
-            for (int r = 0; r < MR_CLUSTER; ++r) *cluster.map_shared_rank(&sm.clu[t & 1][q][tid], r) = v;
-        }
-        mr_cluster_arrive();
-    };
-    // second contraction of tile t: R = sum_q U_q - b (rank order), accumulators += A_tile^T R
-    auto contract2 = [&](int t) {
-        mr_cluster_wait();
-        const int slot = t % a.nstage;
-        const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
-        const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
-        double rlo = 0.0, rhi = 0.0;
-        {
-            const int i0 = fk * 8 + fc, i1 = (fk + 4) * 8 + fc;
-            double s0 = sm.clu[t & 1][0][i0], s1 = sm.clu[t & 1][0][i1];
-#pragma unroll
-            for (int r = 1; r < MR_CLUSTER; ++r) {
-                s0 += sm.clu[t & 1][r][i0];
-                s1 += sm.clu[t & 1][r][i1];
+            if (q == 0) {   // b of this tile was requested one tile ago; request the next one now
+                v -= b_pref;
+                const long long row = lo + static_cast<long long>(t + 1) * MR_TILE + (tid >> 3);
+                b_pref = (row < hi) ? __ldg(a.b + row) : 0.0;
             }
-            rlo = (fk < rows) ? s0 - sm.bt[t & 1][fk] : 0.0;
-            rhi = (fk + 4 < rows) ? s1 - sm.bt[t & 1][fk + 4] : 0.0;
+            const uint32_t off = static_cast<uint32_t>(((buf * MR_CLUSTER + q) * 64 + tid) * 8);
+#pragma unroll
+            for (int r = 0; r < MR_CLUSTER; ++r)
+                mr_st_async(mr_mapa(clu_base + off, r), v, mr_mapa(ubar_base + buf * 8, r));
+        };
+        // second contraction of tile t: R = sum_q (U_q [- b]) in rank order, accumulators += A_tile^T R
+        auto contract2 = [&](int t) {
+            const int buf = t % MR_UBUF;
+            mr_mbar_wait(&sm.ubar[buf], static_cast<uint32_t>(t / MR_UBUF) & 1u);
+            const long long r0 = lo + static_cast<long long>(t) * MR_TILE;
+            const int rows = static_cast<int>(min(static_cast<long long>(MR_TILE), hi - r0));
+            double rlo, rhi;
+            {
+                const int i0 = fk * 8 + fc, i1 = (fk + 4) * 8 + fc;
+                double s0 = sm.clu[buf][0][i0], s1 = sm.clu[buf][0][i1];
+#pragma unroll
+                for (int r = 1; r < MR_CLUSTER; ++r) {
+                    s0 += sm.clu[buf][r][i0];
+                    s1 += sm.clu[buf][r][i1];
+                }
+                rlo = (fk < rows) ? s0 : 0.0;
+                rhi = (fk + 4 < rows) ? s1 : 0.0;
+            }
+            nrm0 = fma(rlo, rlo, nrm0);
+            nrm1 = fma(rhi, rhi, nrm1);
+            if (a.grad) {
+                const unsigned char* base = ring + static_cast<size_t>(slot2) * a.stage_bytes;
+                const double* alo = reinterpret_cast<const double*>(base + static_cast<size_t>(fk) * a.pitch) + warp * CW + fc;
+                const double* ahi = reinterpret_cast<const double*>(base + static_cast<size_t>(fk + 4) * a.pitch) + warp * CW + fc;
+                const bool live_lo = fk < rows, live_hi = fk + 4 < rows;
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                    const double a_lo = live_lo ? alo[8 * m] : 0.0;
+                    const double a_hi = live_hi ? ahi[8 * m] : 0.0;
+                    mr_dmma(acc[m][0], acc[m][1], a_lo, rlo);
+                    mr_dmma(acc[m][0], acc[m][1], a_hi, rhi);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mr_mbar_arrive(&sm.empty[slot2]);   // this warp is done with the tile's slot
+            if (++slot2 == a.nstage) slot2 = 0;
+        };
+
+        if (ntile > 0) {
+            contract1(0);
+            if (warp < 2) publish(0);
         }
-        nrm0 = fma(rlo, rlo, nrm0);
-        nrm1 = fma(rhi, rhi, nrm1);
+        for (int t = 0; t < ntile; ++t) {
+            if (t + 1 < ntile) {
+                contract1(t + 1);
+                if (warp < 2) publish(t + 1);
+            }
+            contract2(t);
+        }
+
+        // ---- results: C fragment -> G[col m0 + fc][lambda 2 fk + {0,1}]
         if (a.grad) {
-            const unsigned char* base = ring + static_cast<size_t>(slot) * a.stage_bytes;
-            const double* alo = reinterpret_cast<const double*>(base + static_cast<size_t>(fk) * a.pitch) + warp * CW + fc;
-            const double* ahi = reinterpret_cast<const double*>(base + static_cast<size_t>(fk + 4) * a.pitch) + warp * CW + fc;
-            const bool live_lo = fk < rows, live_hi = fk + 4 < rows;
+            double* out = a.part + static_cast<size_t>(cl) * MR_NB * a.ldv;
 #pragma unroll
             for (int m = 0; m < MB; ++m) {
-                const double a_lo = live_lo ? alo[8 * m] : 0.0;
-                const double a_hi = live_hi ? ahi[8 * m] : 0.0;
-                mr_dmma(acc[m][0], acc[m][1], a_lo, rlo);
-                mr_dmma(acc[m][0], acc[m][1], a_hi, rhi);
+                const int col = col0 + 8 * m + fc;
+                out[static_cast<size_t>(2 * fk) * a.ldv + col] = acc[m][0];
+                out[static_cast<size_t>(2 * fk + 1) * a.ldv + col] = acc[m][1];
             }
         }
-    };
-
-    // ---- software pipeline: contract1(t+1) runs between arrive(t) ... wait(t)
-    if (ntile > 0) {
-        contract1(0);
-        __syncthreads();
-        publish(0);
-    } else {
-        mr_cluster_arrive();   // keep the cluster barrier phases aligned with the peers (all blocks have the same ntile)
-    }
-    for (int t = 0; t < ntile; ++t) {
-        const bool has_next = t + 1 < ntile;
-        if (has_next) contract1(t + 1);
-        contract2(t);
-        __syncthreads();   // everybody is done with slot t % nstage and with red[(t+1)&1]
-        if (tid == 0 && t + a.nstage < ntile) fill(t + a.nstage);
-        if (has_next) publish(t + 1);
-    }
-    if (ntile == 0) mr_cluster_wait();
-
-    // ---- results: C fragment -> G[col m0 + fc][lambda 2 fk + {0,1}]
-    if (a.grad) {
-        double* out = a.part + static_cast<size_t>(cl) * MR_NB * a.ldv;
-#pragma unroll
-        for (int m = 0; m < MB; ++m) {
-            const int col = col0 + 8 * m + fc;
-            out[static_cast<size_t>(2 * fk) * a.ldv + col] = acc[m][0];
-            out[static_cast<size_t>(2 * fk + 1) * a.ldv + col] = acc[m][1];
+        if (q == 0 && warp == 0) {
+            // lanes with the same fc hold rows fk and fk+4 of column lambda = fc: sum over fk (lane bits 0,1)
+            double v = nrm0 + nrm1;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (fk == 0) a.norms[static_cast<size_t>(cl) * MR_NB + fc] = v;
         }
-    }
-    if (q == 0 && warp == 0) {
-        // lanes with the same fc hold rows fk and fk+4 of column lambda = fc: sum over fk (lane bits 0,1)
-        double v = nrm0 + nrm1;
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (fk == 0) a.norms[static_cast<size_t>(cl) * MR_NB + fc] = v;
     }
     cluster.sync();   // nobody exits while a peer may still write into its shared memory
 }
@@ -416,11 +482,12 @@ extern "C" int fos_mrhs_fista(fos_design* h, const fos_path_params* pp, fos_path
         ma.pitch = pitch;
         ma.part = part;
         ma.norms = norms;
+        ma.prof = nullptr;
         auto launch_pass = [&](const double* Yb, int grad) -> int {
             ma.Y = Yb;
             ma.grad = grad;
             void* params[1] = {&ma};
-            FOS_CUDA(fos_launch_ex(fn, dim3(ncl * MR_CLUSTER), dim3(256), static_cast<size_t>(nstage) * stage_bytes, s, params,
+            FOS_CUDA(fos_launch_ex(fn, dim3(ncl * MR_CLUSTER), dim3(MR_THREADS), static_cast<size_t>(nstage) * stage_bytes, s, params,
                                    false, 0));
             h->launches++;
             return FOS_OK;

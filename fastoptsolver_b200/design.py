@@ -47,6 +47,21 @@ class DeviceDesign:
     # ------------------------------------------------------------------ constructors
     @classmethod
     def from_host(cls, A, b, device=0):
+        des, upload = cls.begin_from_host(A, b, device=device)
+        try:
+            upload()
+        except Exception:
+            des.close()
+            raise
+        return des
+
+    @classmethod
+    def begin_from_host(cls, A, b, device=0):
+        """Two-step creation (include/fos.h: fos_design_create_begin / fos_design_upload): returns the
+        design with its matrix still undefined and a callable that performs the copy (it may run on
+        another thread; ctypes releases the GIL).  Row-sharded callers wire the exchange windows of the
+        handle meanwhile (multigpu.sharded_from_host).  Nothing else may use the design before the
+        callable has returned."""
         lib = _lib.load()
         A = np.asarray(A)
         if A.ndim != 2:
@@ -69,8 +84,13 @@ class DeviceDesign:
         if b.shape[0] != n:
             raise ValueError(f"b has {b.shape[0]} entries, A has {n} rows")
         out = C.c_void_p()
-        _lib.check(lib.fos_design_create(_ptr(A), _ptr(b), n, d, _DTYPES[A.dtype], rs, cs, device, C.byref(out)))
-        return cls(out.value, n, d, _DTYPES[A.dtype], device)
+        _lib.check(lib.fos_design_create_begin(n, d, _DTYPES[A.dtype], device, C.byref(out)))
+        des = cls(out.value, n, d, _DTYPES[A.dtype], device)
+
+        def upload(A=A, b=b, rs=rs, cs=cs):      # keeps the (possibly converted) host arrays alive until done
+            _lib.check(lib.fos_design_upload(des.handle, _ptr(A), _ptr(b), rs, cs))
+
+        return des, upload
 
     @classmethod
     def synthetic(cls, n, d, dtype=np.float64, seed=0, noise_std=1.0, rho1=0.8, rho2=0.9, row0=0, device=0):

@@ -231,15 +231,42 @@ def sharded_from_host(A_local, b_local, dist, group=None, device=None):
     if device is None:
         import torch
         device = torch.cuda.current_device()
-    des = DeviceDesign.from_host(A_local, b_local, device=device)
+    import threading
+    # The PCIe copy runs on a side thread (ctypes releases the GIL) while this thread wires the exchange
+    # windows of the same handle: socket hand-off of the descriptors + two object all-gathers, ~0.1 s
+    # that used to FOLLOW the copy (the windows do not depend on the data).
+    des, upload = DeviceDesign.begin_from_host(A_local, b_local, device=device)
+    failure = []
+
+    def run():
+        try:
+            upload()
+        except BaseException as e:      # re-raised on the caller's thread below
+            failure.append(e)
+
+    th = threading.Thread(target=run, name="fos-upload")
+    th.start()
+    wiring_error = None
+    try:
+        attach(des, dist, group)
+    except BaseException as e:
+        wiring_error = e
+    th.join()
+    if wiring_error is not None:        # the collective itself broke: nothing to agree on any more
+        des.close()
+        raise wiring_error
+    # one more (tiny) all-gather: did every rank's copy succeed, and does every rank hold a Gram matrix
+    have = (not failure) and des.upload_gram()["state"] == 1
+    everyone = _gather((not failure, have), dist, group)
+    if not all(ok for ok, _ in everyone):
+        des.close()
+        raise failure[0] if failure else RuntimeError("the upload failed on another rank")
     # Every rank accumulated the Gram matrix of its own rows under the upload (include/fos.h,
     # fos_design_upload_gram)?  Then estimate_lipschitz iterates on them -- local product, then the
     # same fused peer-memory all-reduce of the d-vector as a streaming pass; the matrices are never
     # summed.  All ranks must take the same branch: if any rank has none (shard below the size
     # threshold, workspace allocation failed), all discard theirs and keep streaming.
-    have = des.upload_gram()["state"] == 1
-    everyone = attach(des, dist, group, piggyback=have)
-    if all(everyone):
+    if all(h for _, h in everyone):
         des.set_upload_gram(2)
     elif have:
         des.set_upload_gram(0)

@@ -82,6 +82,13 @@ int fos_trim(void);
  * C-order is (d, 1) and Fortran order is (1, n).  The host arrays are never written. */
 int fos_design_create(const void* A, const double* b, int64_t n, int64_t d, int dtype,
                       int64_t row_stride, int64_t col_stride, int device, fos_design** out);
+/* Two-step form of fos_design_create: _begin allocates the design (matrix undefined), _upload copies the
+ * host arrays into it (same layouts and staging as fos_design_create).  Between the two calls the handle
+ * may already be wired to its peers (fos_comm_window_alloc* / fos_comm_attach* from another host thread):
+ * row-sharded callers overlap the window hand-off with the PCIe copy.  Solver entry points must not be
+ * called before _upload has returned. */
+int fos_design_create_begin(int64_t n, int64_t d, int dtype, int device, fos_design** out);
+int fos_design_upload(fos_design* h, const void* A, const double* b, int64_t row_stride, int64_t col_stride);
 /* Borrow a row-major matrix already resident on `device` (lda in elements, lda*elem
  * multiple of 16 bytes, base 16-byte aligned); b_dev is float64.  Not freed by destroy. */
 int fos_design_create_device(const void* A_dev, const double* b_dev, int64_t n, int64_t d,
