@@ -364,6 +364,31 @@ def host_copy_of(des, pinned=True):
     return A_h, b_h
 
 
+def h2d_ceiling(ctx, A_h):
+    """What the box gives a plain pinned -> HBM copy of the same host buffer, all ranks copying at the
+    same moment (best of 2): the ceiling the upload inside the end-to-end call is measured against."""
+    import torch
+    src = torch.from_numpy(A_h)
+    dev = torch.device("cuda", ctx.device)
+    dst = torch.empty(src.shape, dtype=src.dtype, device=dev)
+    best = None
+    for _ in range(2):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    del dst
+    torch.cuda.empty_cache()
+    mine = src.numel() * src.element_size() / best / 1e9
+    out = {"GBps_this_rank": mine, "what": "dst.copy_(pinned_src) of this rank's rows, all ranks at once, best of 2"}
+    if ctx.dist is not None:
+        per = [v[0] for v in ctx.gather_floats([mine])]
+        out.update({"GBps_per_rank_min": min(per), "GBps_per_rank_max": max(per), "GBps_aggregate": sum(per)})
+    return out
+
+
 # =============================================================================== c3 / c2
 def parity_record(ctx):
     """One golden trace of the UNMODIFIED reference (tests/golden/traces_wide.npz, written by
@@ -661,6 +686,12 @@ def e2e_fista(ctx, des, alpha1, K, pinned=True, reps=3):
         if shard is not None:
             dist.barrier()
             shard.close()
+    ceiling = None
+    if pinned:
+        try:
+            ceiling = h2d_ceiling(ctx, A_h)
+        except Exception as e:          # extra information only
+            ceiling = {"error": f"{type(e).__name__}: {e}"[:200]}
     walls = [r["wall"] for r in runs]
     r = runs[int(np.argsort(walls)[len(walls) // 2])]          # the median run, reported in full
     wall, upload_s, gram_info, info, lip = r["wall"], r["upload_s"], r["gram_info"], r["info"], r["lip"]
@@ -669,6 +700,9 @@ def e2e_fista(ctx, des, alpha1, K, pinned=True, reps=3):
     return {"value": K / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
             "wall_s": wall, "walls_s": walls, "value_is": f"K / median wall time of {reps} calls",
             "upload_s": upload_s, "h2d_GBps": (h2d / upload_s / 1e9) if upload_s else None,
+            "h2d_ceiling": ceiling,
+            "upload_frac_of_ceiling": ((h2d / upload_s / 1e9) / ceiling["GBps_this_rank"]) if (
+                upload_s and ceiling and ceiling.get("GBps_this_rank")) else None,
             "loop_ms": info["loop_ms"], "lipschitz_ms": lip["gpu_ms"],
             "lipschitz_iters": lip["iters"], "lipschitz_via": lip.get("via"),
             "upload_gram": {k: gram_info.get(k) for k in ("state", "copy_ms", "tail_ms")},
