@@ -534,7 +534,6 @@ def bench_fista(ctx, cfg_name):
     lda = d + (d % 2)
     rows_local = hi - lo
     alg_bytes = rows_local * lda * 8 + rows_local * 8
-    fused = int(info["kernel_launches"]) == 1      # the whole K-step solve was ONE launch of the persistent kernel
     if fused:
         # the dominant kernel IS the timed region: bytes per launch = passes x algorithmic bytes of a pass,
         # duration = the CUDA-event pair around the launch on the solver stream (the `value` measurement)
@@ -546,10 +545,15 @@ def bench_fista(ctx, cfg_name):
         k_ms = pinfo["grad_kernel_ms"] / k_launch
         alg_bytes_launch = alg_bytes
     achieved = alg_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    fused = int(info["kernel_launches"]) == 1      # the whole K-step solve was ONE launch of the persistent kernel
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "grad_kernel_traffic.json"))).get(
-            f"{rows_local}x{d}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "grad_kernel_traffic.json")))
+        if fused:   # ncu measured one launch of 4 passes; per launch here = per-pass figure x this launch's passes
+            per_pass = tj.get(f"solve:{rows_local}x{d}:per_pass")
+            traffic = per_pass * int(info["passes"]) if per_pass else None
+        else:
+            traffic = tj.get(f"{rows_local}x{d}")
     except Exception:
         pass
     kname = {4096: "<double,256,16,1>", 2048: "<double,256,8,2>"}.get(d, "<double,...>")
@@ -557,7 +561,7 @@ def bench_fista(ctx, cfg_name):
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
-                "traffic": (traffic * int(info["passes"])) if (traffic and fused) else traffic,
+                "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "kernel_ms_avg": k_ms, "launches_timed": k_launch,
                 "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None}
     if fused:
