@@ -1468,6 +1468,30 @@ int fos_solve_stages(const fos_design* h) {
     return ns >= 2 ? static_cast<int>(ns) : 0;
 }
 
+// Row-sharded designs: every rank must take the SAME path (the persistent kernel pushes slices, the
+// epilogue kernel pulls vectors; mixing them deadlocks until the wait deadlines fire).  The ranks therefore
+// agree once, when the windows are attached (multigpu.attach): a rank is a candidate if its design
+// qualifies with a margin that survives the rate-weighted re-partition (blocks between 0.3 x and 1.6 x the
+// mean from 4 ranks on), and the kernel is used only if ALL ranks are candidates.
+extern "C" int fos_design_solve_kernel_ok(const fos_design* h, int world, int* ok) {
+    FOS_REQUIRE(h && ok, "null pointer argument");
+    *ok = 0;
+    if (!h->fused_ok || h->kern_kind != 1 || h->gsync == nullptr) return FOS_OK;
+    StreamCfg cfg;
+    if (!pick_stream_cfg(h->dtype, h->lda, &cfg)) return FOS_OK;
+    const char* e = getenv("FOS_BALANCE");
+    const bool may_rebalance = (world >= 4 && !(e && e[0] == '0')) || (e && e[0] == '1');
+    const long long need = (may_rebalance ? 8LL : 2LL) * cfg.r;
+    *ok = (h->n / h->n_parts >= need) ? 1 : 0;
+    return FOS_OK;
+}
+
+extern "C" int fos_design_solve_kernel_disable(fos_design* h) {
+    FOS_REQUIRE(h, "null design");
+    h->fused_ok = false;
+    return FOS_OK;
+}
+
 int fos_launch_solve(fos_design* h, const FosHist& hist, long long max_passes) {
     int nstage = fos_solve_stages(h);
     if (nstage == 0) {

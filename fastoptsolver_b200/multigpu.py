@@ -216,9 +216,16 @@ def attach(des: DeviceDesign, dist, group=None, piggyback=None):
         blob = C.create_string_buffer(b"".join(handles), 64 * world)
         _lib.check(lib.fos_comm_attach(des.handle, blob, world))
 
+    # Persistent solve kernel (push-model exchange) or launch pairs (pull-model): the same on every rank.
+    # The candidate flag rides on the closing all-gather of the wiring.
+    ok = C.c_int(0)
+    _lib.check(lib.fos_design_solve_kernel_ok(des.handle, world, C.byref(ok)))
     kind, extras = share_windows(alloc_fd, attach_fd, lambda: _lib.check(lib.fos_comm_window_free(des.handle)),
-                                 alloc_ipc, attach_ipc, dist, group, piggyback,
+                                 alloc_ipc, attach_ipc, dist, group, (bool(ok.value), piggyback),
                                  prefer_vmm=os.environ.get("FOS_COMM", "vmm") != "ipc")
+    if not all(f for f, _ in extras):
+        _lib.check(lib.fos_design_solve_kernel_disable(des.handle))
+    extras = [p for _, p in extras]
     des.comm_kind = kind
     if hasattr(des, "_life"):
         des._life["sharded"] = world > 1      # reclaiming it without multigpu.close() warns

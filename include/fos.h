@@ -139,6 +139,11 @@ int fos_design_set_profile(fos_design* h, int enable);
 int fos_time_grad_kernel(fos_design* h, int mode, int reps, float* ms_avg);
 /* Debug: per-CTA start/end timestamps (ns) of one gradient-kernel launch; out[2*n_parts]. */
 int fos_debug_cta_times(fos_design* h, int mode, long long* out, int cap, int* n_parts);
+/* Row-sharded designs: may this rank run its solves in the persistent solve kernel (one launch per solve,
+ * push-model slice exchange)?  All ranks must take the same path, so the binding gathers this flag over
+ * the ranks when the windows are attached and calls _disable everywhere unless every rank said yes. */
+int fos_design_solve_kernel_ok(const fos_design* h, int world, int* ok);
+int fos_design_solve_kernel_disable(fos_design* h);
 /* Debug: phase profile of the persistent solve kernel (CTA 0's %globaltimer stamps, ns, accumulated
  * since the design was created): out[0..7] = streaming loop, wait at barrier 1, slice sums, peer exchange,
  * elementwise 1, barrier 2, scalars + decision + elementwise 2 + commit, barrier 3; out[8] = passes.
