@@ -530,6 +530,7 @@ def bench_fista(ctx, cfg_name):
     value = K / (loop_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the fused gradient pass)
+    fused = int(info["kernel_launches"]) == 1      # the whole K-step solve was ONE launch of the persistent kernel
     peak, peak_src = hbm_peak()
     lda = d + (d % 2)
     rows_local = hi - lo
@@ -545,7 +546,6 @@ def bench_fista(ctx, cfg_name):
         k_ms = pinfo["grad_kernel_ms"] / k_launch
         alg_bytes_launch = alg_bytes
     achieved = alg_bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    fused = int(info["kernel_launches"]) == 1      # the whole K-step solve was ONE launch of the persistent kernel
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "grad_kernel_traffic.json")))
