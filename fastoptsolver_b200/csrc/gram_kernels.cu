@@ -162,7 +162,16 @@ __global__ void gram_reduce_kernel(const double* __restrict__ W, double* __restr
 // batched path iteration: out tile PM (i) x 64 (l), K chunks of 16.  PM = 128 when there are
 // enough penalties to fill the SMs, 64 / 32 for short penalty lists (more, smaller tiles).
 // ------------------------------------------------------------------------------------------
-constexpr int PN = 64, PK = 16, PLD = PK + 4, PSTAGES = 4;
+#ifndef FOS_PATH_PK
+#define FOS_PATH_PK 16
+#endif
+#ifndef FOS_PATH_STAGES
+#define FOS_PATH_STAGES 4
+#endif
+// k-chunk 16 x 4 stages; 32 x 3 stages (half as many block barriers) measured the same on the tile schedule and
+// slower on the stream-K schedule (coarser ranges, longer pipeline prologue per segment): -DFOS_PATH_PK=32 -DFOS_PATH_STAGES=3
+constexpr int PN = 64, PK = FOS_PATH_PK, PLD = PK + 4, PSTAGES = FOS_PATH_STAGES;
+constexpr int PCPR = PK / 2;   // 16-byte chunks per tile row and stage
 
 struct PathArgs {
     const double* G;      // [d][d] row-major, symmetric
@@ -178,27 +187,30 @@ struct PathArgs {
     double* step_part;    // [d/PM][Lpad]: sum_i (x+ - x)^2 partials (nullable: not a check iteration)
 };
 
+// Shared by the tile-per-CTA kernel and the stream-K kernel: the pipelined contraction of one
+// (PM x PN) tile over the k-steps [ks_lo, ks_lo + nst) and the fused epilogue on a finished tile.
 template <int PM>
-__global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
-    constexpr int WI = PM / 32;          // warps along i
-    constexpr int WL = 8 / WI;           // warps along l
-    constexpr int LW = PN / WL;          // l columns per warp
-    constexpr int NJ = LW / 8;           // mma blocks along l per warp
-    constexpr int CH = (PM + PN) * 8 / 256;  // 16-byte chunks per thread and stage
-    extern __shared__ __align__(16) double smem[];  // [PSTAGES][(PM+PN)][PLD]
-    __shared__ double part[8][LW][4];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i0 = blockIdx.x * PM, l0 = blockIdx.y * PN;
-    const int nst = p.d / PK;
+struct PathTile {
+    static constexpr int WI = PM / 32;          // warps along i
+    static constexpr int WL = 8 / WI;           // warps along l
+    static constexpr int LW = PN / WL;          // l columns per warp
+    static constexpr int NJ = LW / 8;           // mma blocks along l per warp
+    static constexpr int CH = (PM + PN) * PCPR / 256;  // 16-byte chunks per thread and stage
+};
 
+template <int PM>
+__device__ __forceinline__ void path_mainloop(const PathArgs& p, double* smem, int i0, int l0, int ks_lo, int nst,
+                                              double (&acc)[4][PathTile<PM>::NJ][2]) {
+    constexpr int WL = PathTile<PM>::WL, LW = PathTile<PM>::LW, NJ = PathTile<PM>::NJ, CH = PathTile<PM>::CH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto issue = [&](int st) {
         if (st < nst) {
             double* base = smem + static_cast<size_t>(st % PSTAGES) * ((PM + PN) * PLD);
-            const int k0 = st * PK;
+            const int k0 = (ks_lo + st) * PK;
 #pragma unroll
             for (int q = 0; q < CH; ++q) {
                 const int chunk = tid + 256 * q;
-                const int row = chunk >> 3, c16 = chunk & 7;
+                const int row = chunk / PCPR, c16 = chunk % PCPR;
                 const double* src = (row < PM) ? p.G + static_cast<size_t>(i0 + row) * p.d + k0 + c16 * 2
                                                : p.Yin + static_cast<size_t>(l0 + row - PM) * p.d + k0 + c16 * 2;
                 cp_async16(base + row * PLD + c16 * 2, src, 16);
@@ -206,8 +218,6 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
         }
         cp_async_commit();
     };
-
-    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -237,7 +247,17 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
         }
     }
     cp_async_wait<0>();
+    __syncthreads();   // the ring may be refilled by the next tile of the same CTA
+}
 
+// iblk: index of the tile's i-block (row of the partial-sum arrays)
+template <int PM>
+__device__ __forceinline__ void path_epilogue(const PathArgs& p, int i0, int l0, int iblk,
+                                              double (&acc)[4][PathTile<PM>::NJ][2], double (*part)[PathTile<PM>::LW][4]) {
+    constexpr int WI = PathTile<PM>::WI, WL = PathTile<PM>::WL, LW = PathTile<PM>::LW, NJ = PathTile<PM>::NJ;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wi = warp / WL, wl = warp % WL;
+    const int fk = lane & 3, fc = lane >> 2;
     // per-(l) sums of this thread: [0..3] objective pieces (mode 1) or [0] squared step (mode 0)
     double sums[NJ][2][4];
 #pragma unroll
@@ -307,9 +327,108 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
 #pragma unroll
     for (int w = 0; w < WI; ++w) t += part[w * WL + wl2][lw][q];
     if (p.mode == 0) {
-        if (q == 0) p.step_part[static_cast<size_t>(blockIdx.x) * p.Lpad + l0 + l_loc] = t;
+        if (q == 0) p.step_part[static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc] = t;
     } else {
-        p.obj_part[(static_cast<size_t>(blockIdx.x) * p.Lpad + l0 + l_loc) * 4 + q] = t;
+        p.obj_part[(static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc) * 4 + q] = t;
+    }
+}
+
+template <int PM>
+__global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
+    extern __shared__ __align__(16) double smem[];  // [PSTAGES][(PM+PN)][PLD]
+    __shared__ double part[8][PathTile<PM>::LW][4];
+    const int i0 = blockIdx.x * PM, l0 = blockIdx.y * PN;
+    double acc[4][PathTile<PM>::NJ][2];
+    path_mainloop<PM>(p, smem, i0, l0, 0, p.d / PK, acc);
+    path_epilogue<PM>(p, i0, l0, blockIdx.x, acc, part);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stream-K schedule of the same iteration (128 x 64 tiles): the T tiles x d/16 k-steps are cut into P
+// equal contiguous ranges, one per CTA (P = number of SMs), so every SM works the whole time whatever
+// the tile count -- 128 tiles on 148 SMs at 256 penalties, 32 tiles at the 32 penalties a rank holds
+// on 8 GPUs.  A CTA whose range covers a whole tile finishes it in registers.  A partial range is
+// written to the workspace and counted on the tile; the LAST contributor to arrive (atomic ticket, no
+// waiting, no co-residency assumption) adds the contributors' partials in ascending CTA order -- the
+// same order whoever arrives last, so results stay bit-reproducible -- and runs the fused epilogue.
+// ------------------------------------------------------------------------------------------
+struct PathSkArgs {
+    PathArgs p;
+    double* W;            // [P][2][32][256] double: partial accumulators (fragment layout), 2 slots per CTA
+    unsigned* ticket;     // [T] arrivals per tile (reset by the finishing CTA)
+    int T, KT, P;         // tiles, k-steps per tile, CTAs
+};
+
+__device__ __forceinline__ long long sk_begin(const PathSkArgs& a, int c) {
+    return (static_cast<long long>(a.T) * a.KT * c) / a.P;
+}
+
+__global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a) {
+    constexpr int PM = 128;
+    constexpr int NJ = PathTile<PM>::NJ;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double part[8][PathTile<PM>::LW][4];
+    __shared__ unsigned s_ticket;
+    const PathArgs& p = a.p;
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x;
+    const int nlb = p.Lpad / PN;                 // l-blocks; tile t = (iblk = t / nlb, lblk = t % nlb)
+    const long long r0 = sk_begin(a, c), r1 = sk_begin(a, c + 1);
+    double acc[4][NJ][2];
+    for (long long r = r0; r < r1;) {
+        const int t = static_cast<int>(r / a.KT);
+        const int k_lo = static_cast<int>(r - static_cast<long long>(t) * a.KT);
+        const int k_hi = static_cast<int>(min(static_cast<long long>(a.KT), r1 - static_cast<long long>(t) * a.KT));
+        const int iblk = t / nlb, i0 = iblk * PM, l0 = (t % nlb) * PN;
+        path_mainloop<PM>(p, smem, i0, l0, k_lo, k_hi - k_lo, acc);
+        if (k_lo == 0 && k_hi == a.KT) {
+            path_epilogue<PM>(p, i0, l0, iblk, acc, part);
+        } else {
+            // publish the partial (slot = 0 for a range that starts inside a tile, 1 for the one that ends inside)
+            const int slot = (k_lo != 0) ? 0 : 1;
+            double2* w = reinterpret_cast<double2*>(a.W + (static_cast<size_t>(c) * 2 + slot) * (PM * PN));
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) w[(i * NJ + j) * 256 + tid] = make_double2(acc[i][j][0], acc[i][j][1]);
+            __threadfence();
+            __syncthreads();
+            // contributors of tile t: the CTAs whose ranges intersect [t KT, (t+1) KT)
+            const long long tb = static_cast<long long>(t) * a.KT, te = tb + a.KT;
+            int c_first = static_cast<int>((tb * a.P) / (static_cast<long long>(a.T) * a.KT));
+            while (sk_begin(a, c_first + 1) <= tb) ++c_first;
+            while (c_first > 0 && sk_begin(a, c_first) > tb) --c_first;
+            int c_last = c_first;
+            while (c_last + 1 < a.P && sk_begin(a, c_last + 1) < te) ++c_last;
+            const unsigned ncontrib = static_cast<unsigned>(c_last - c_first + 1);
+            if (tid == 0) s_ticket = atomicAdd(&a.ticket[t], 1u);
+            __syncthreads();
+            if (s_ticket == ncontrib - 1) {   // last to arrive: every partial of this tile is in memory
+                __threadfence();
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int cc = c_first; cc <= c_last; ++cc) {
+                    // slot 0: the contributor's range STARTS inside this tile; slot 1: it starts at or before the
+                    // tile's first k-step (and ends inside it) -- the rule the contributors used above
+                    const int slot_cc = (sk_begin(a, cc) > tb) ? 0 : 1;
+                    const double2* wv = reinterpret_cast<const double2*>(a.W + (static_cast<size_t>(cc) * 2 + slot_cc) * (PM * PN));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            const double2 v = __ldcg(&wv[(i * NJ + j) * 256 + tid]);
+                            acc[i][j][0] += v.x;
+                            acc[i][j][1] += v.y;
+                        }
+                }
+                if (tid == 0) a.ticket[t] = 0u;   // ready for the next launch
+                path_epilogue<PM>(p, i0, l0, iblk, acc, part);
+            }
+            __syncthreads();
+        }
+        r = static_cast<long long>(t) * a.KT + k_hi;
     }
 }
 
@@ -937,6 +1056,27 @@ static cudaError_t launch_path(const PathArgs& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// stream-K launch (128 x 64 tiles only); W and ticket are owned by the caller
+static cudaError_t launch_path_sk(const PathArgs& p, double* W, unsigned* ticket, int P, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(PSTAGES) * (128 + PN) * PLD * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    PathSkArgs a;
+    a.p = p;
+    a.W = W;
+    a.ticket = ticket;
+    a.T = (p.d / 128) * (p.Lpad / PN);
+    a.KT = p.d / PK;
+    a.P = P;
+    path_step_sk_kernel<<<dim3(P), dim3(256), smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_path_pm(int pm, const PathArgs& p, cudaStream_t st) {
     if (pm == 128) return launch_path<128>(p, st);
     if (pm == 64) return launch_path<64>(p, st);
@@ -953,15 +1093,26 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
     // i-tile: the largest that still gives every SM a tile
     int pm = 128;
     while (pm > 32 && static_cast<long long>(d / pm) * (Lpad / PN) < 120) pm /= 2;
+    // Stream-K over 128 x 64 tiles whenever the tile count does not fill the SMs in whole waves (FOS_PATH_SK=0/1
+    // forces the choice): every SM gets the same number of k-steps whatever the number of penalties.
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device);
+    const long long tiles128 = static_cast<long long>(d / 128) * (Lpad / PN);
+    bool use_sk = d % 128 == 0 && tiles128 * (d / PK) >= 4LL * sm_count && tiles128 <= 4LL * sm_count;
+    if (const char* e = getenv("FOS_PATH_SK")) use_sk = use_sk && e[0] != '0';
+    if (use_sk) pm = 128;
     const int nblk = d / pm;
     const size_t mat = static_cast<size_t>(Lpad) * d;
     double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr,
            *spart = nullptr, *smax = nullptr;
     double* smax_host = nullptr;
+    double* skW = nullptr;
+    unsigned* sk_ticket = nullptr;
     auto cleanup = [&]() {
-        for (double* q : {Y0, Y1, X, a1, part, obj, spart, smax})
+        for (double* q : {Y0, Y1, X, a1, part, obj, spart, smax, skW})
             fos_pool_free(q);
         fos_pool_free(smax_host);
+        fos_pool_free(sk_ticket);
     };
     auto body = [&]() -> int {
         FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&Y0), mat * sizeof(double)));
@@ -973,6 +1124,11 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&obj), Lpad * sizeof(double)));
         FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&smax), sizeof(double)));
         FOS_CUDA(fos_pool_malloc_host(reinterpret_cast<void**>(&smax_host), sizeof(double)));
+        if (use_sk) {
+            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&skW), static_cast<size_t>(sm_count) * 2 * 128 * PN * sizeof(double)));
+            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&sk_ticket), static_cast<size_t>(tiles128) * sizeof(unsigned)));
+            FOS_CUDA(cudaMemsetAsync(sk_ticket, 0, static_cast<size_t>(tiles128) * sizeof(unsigned), g->stream));
+        }
         FOS_CUDA(cudaMemsetAsync(Y0, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(Y1, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(X, 0, mat * sizeof(double), g->stream));
@@ -1010,7 +1166,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
             p.Yout = (k & 1) ? Y0 : Y1;
             const bool check = pp->tol > 0.0 && ((k + 1) % pp->check_every == 0);
             p.step_part = check ? spart : nullptr;
-            FOS_CUDA(launch_path_pm(pm, p, g->stream));
+            FOS_CUDA(use_sk ? launch_path_sk(p, skW, sk_ticket, sm_count, g->stream) : launch_path_pm(pm, p, g->stream));
             ++n_launch;
             ++iters;
             if (check) {
@@ -1028,7 +1184,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         p.Yin = X;
         p.Yout = nullptr;
         p.step_part = nullptr;
-        FOS_CUDA(launch_path_pm(pm, p, g->stream));
+        FOS_CUDA(use_sk ? launch_path_sk(p, skW, sk_ticket, sm_count, g->stream) : launch_path_pm(pm, p, g->stream));
         path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, nblk, Lpad, a1, pp->alpha2,
                                                                                    0.5 * g->bb, obj);
         n_launch += 2;

@@ -215,3 +215,37 @@ def test_screened_path_matches_unscreened_on_device():
         assert np.linalg.norm(Xa[j] - Xw[j]) <= 1e-9 * max(np.linalg.norm(Xw[j]), 1e-3 * scale), j
     gram.close()
     des.close()
+
+
+@pytest.mark.parametrize("d,n_lambda", [(1024, 70), (1024, 200), (2048, 33), (4096, 32)])
+def test_stream_k_schedule_matches_tile_schedule(d, n_lambda, monkeypatch):
+    """The stream-K schedule of the batched iteration (equal k-step ranges per SM, partial tiles combined by
+    the last contributor in CTA order) against the one-tile-per-CTA schedule: same iterates to 1e-12 (the
+    k-sums associate differently), same objectives, same stop iteration; bit-identical from run to run;
+    and every column against the reference's fista (via the oracle) to 1e-9."""
+    import oracle
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    A, b = _design(3 * d, d, 11)
+    lam = float(np.max(np.abs(A.T @ b)))
+    alphas = lam * np.logspace(-0.3, -1.8, n_lambda)
+    np.random.seed(0)
+    L = oracle.estimate_lipschitz(A)
+    des = DeviceDesign.from_host(A, b)
+    gram = GM.GramDesign(des)
+    out = {}
+    for sk in ("1", "0", "1"):
+        monkeypatch.setenv("FOS_PATH_SK", sk)
+        X, info = GM.fista_path(des, None, alphas, alpha2=0.01 * lam, max_iter=30, L=L + 0.01 * lam, gram=gram)
+        Xt, it = GM.fista_path(des, None, alphas[:5], max_iter=4000, L=L, gram=gram, tol=1e-7, check_every=10)
+        out.setdefault(sk, []).append((X, info["obj"], Xt, it["iters"]))
+    (Xa, oa, Xta, ita), (Xb, ob, Xtb, itb) = out["1"][0], out["0"][0]
+    assert harness.rel_err(Xa, Xb) <= 1e-12 and harness.rel_err(oa, ob) <= 1e-12
+    assert ita == itb and harness.rel_err(Xta, Xtb) <= 1e-9
+    assert out["1"][1][0].tobytes() == Xa.tobytes()
+    for j in (0, n_lambda // 2, n_lambda - 1):
+        np.random.seed(0)
+        x_ref = oracle.fista(A, b, "elasticnet", alphas[j], 0.01 * lam, max_iter=30)
+        assert harness.rel_err(Xa[j], x_ref) <= 1e-9, j
+    gram.close()
+    des.close()
