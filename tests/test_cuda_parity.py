@@ -160,7 +160,7 @@ def test_persistent_solve_kernel_at_scale(monkeypatch):
         res = {}
         for fused in ("1", "0", "1"):
             monkeypatch.setenv("FOS_FUSED", fused)
-            d2 = DeviceDesign.from_device_pointers(*des_pointers(des), des.shape[0], des.shape[1], des.dtype, des.shape[1],
+            d2 = DeviceDesign.from_device_pointers(*des_pointers(des), des.shape[0], des.shape[1], des.dtype, _lda(des),
                                                    keepalive=des)
             np.random.seed(0)
             if kind == "fista":
@@ -180,6 +180,62 @@ def test_persistent_solve_kernel_at_scale(monkeypatch):
         xc, hc, lsc, itc = res["1"][1]
         assert xc.tobytes() == xa.tobytes() and np.asarray(hc["obj"]).tobytes() == np.asarray(ha["obj"]).tobytes()
     des.close()
+
+
+@pytest.mark.parametrize("n,d,dtype", [(30000, 1500, np.float32), (20000, 4100, np.float64), (20000, 8192, np.float32),
+                                       (50000, 641, np.float64), (9000, 2048, np.float64)])
+def test_persistent_solve_kernel_shapes(n, d, dtype, monkeypatch):
+    """The persistent kernel on the other streaming builds: fp32 storage, odd d (padded leading dimension,
+    a last column pair that is half padding), d > 4096 (512-thread build, 28 column pairs per CTA slice),
+    short row blocks (ring shallower than the shared-memory budget).  Against the two-launch path (1e-12) for
+    fista with Armijo and fista_delta with a fixed step, and against the oracle on a downloaded row block."""
+    import oracle
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200.design import DeviceDesign
+    des = DeviceDesign.synthetic(n, d, dtype, seed=4, noise_std=0.5, rho1=0.5, rho2=0.7)
+    des.standardize()
+    a1 = 0.05 * des.lambda_max()
+    runs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("FOS_FUSED", fused)
+        d2 = DeviceDesign.from_device_pointers(*des_pointers(des), n, d, des.dtype, _lda(des), keepalive=des)
+        np.random.seed(0)
+        xa, ha = S.fista(d2, None, "elasticnet", a1, 0.02 * a1, max_iter=12, backtracking=True, t_init_factor=2.0,
+                         return_history=True)
+        la = list(S.ls_call_iters)
+        launches = S.last_run["solver"]["kernel_launches"]
+        np.random.seed(0)
+        xb, hb = S.fista_delta(d2, None, "lasso", a1, 0.0, 3.0, max_iter=12, return_history=True)
+        assert (launches == 1) == (fused == "1"), (fused, launches)
+        runs[fused] = (xa, ha, la, xb, hb)
+        d2.close()
+    (xa, ha, la, xb, hb), (ya, ga, ma, yb, gb) = runs["1"], runs["0"]
+    assert la == ma
+    assert harness.rel_err(xa, ya) <= 1e-12 and harness.rel_err(ha["obj"], ga["obj"]) <= 1e-12
+    assert harness.rel_err(xb, yb) <= 1e-12 and harness.rel_err(hb["obj"], gb["obj"]) <= 1e-12
+    assert not np.any(np.isnan(xa)) and xa.shape == (d,)
+    # a row block small enough for the oracle, solved by the persistent kernel again
+    rows = 3000
+    A_blk, b_blk = des.download(0, rows)
+    monkeypatch.setenv("FOS_FUSED", "1")
+    blk = DeviceDesign.from_host(A_blk, b_blk)
+    a1b = 0.05 * blk.lambda_max()
+    np.random.seed(0)
+    x_dev, h_dev = S.fista(blk, None, "lasso", a1b, 0.0, max_iter=15, return_history=True)
+    np.random.seed(0)
+    x_ref, h_ref = oracle.fista(np.asarray(A_blk, dtype=np.float64), b_blk, "lasso", a1b, 0.0, max_iter=15, return_history=True)
+    assert harness.rel_err(x_dev, x_ref) <= 1e-10
+    np.testing.assert_allclose(h_dev["obj"], h_ref["obj"], rtol=1e-10)
+    blk.close()
+    des.close()
+
+
+def _lda(des):
+    import ctypes as C
+    from fastoptsolver_b200 import _lib
+    n, d, dt, lda = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+    _lib.check(_lib.load().fos_design_shape(des.handle, C.byref(n), C.byref(d), C.byref(dt), C.byref(lda)))
+    return lda.value
 
 
 def des_pointers(des):
