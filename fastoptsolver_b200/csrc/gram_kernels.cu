@@ -189,23 +189,24 @@ struct PathArgs {
 
 // Shared by the tile-per-CTA kernel and the stream-K kernel: the pipelined contraction of one
 // (PM x PN) tile over the k-steps [ks_lo, ks_lo + nst) and the fused epilogue on a finished tile.
-template <int PM>
+template <int PM, int TN = PN>
 struct PathTile {
     static constexpr int WI = PM / 32;          // warps along i
     static constexpr int WL = 8 / WI;           // warps along l
-    static constexpr int LW = PN / WL;          // l columns per warp
+    static constexpr int LW = TN / WL;          // l columns per warp
     static constexpr int NJ = LW / 8;           // mma blocks along l per warp
-    static constexpr int CH = (PM + PN) * PCPR / 256;  // 16-byte chunks per thread and stage
+    static constexpr int CH = (PM + TN) * PCPR / 256;  // 16-byte chunks per thread and stage
 };
 
-template <int PM>
+template <int PM, int TN = PN>
 __device__ __forceinline__ void path_mainloop(const PathArgs& p, double* smem, int i0, int l0, int ks_lo, int nst,
-                                              double (&acc)[4][PathTile<PM>::NJ][2]) {
-    constexpr int WL = PathTile<PM>::WL, LW = PathTile<PM>::LW, NJ = PathTile<PM>::NJ, CH = PathTile<PM>::CH;
+                                              double (&acc)[4][PathTile<PM, TN>::NJ][2]) {
+    using PT = PathTile<PM, TN>;
+    constexpr int WL = PT::WL, LW = PT::LW, NJ = PT::NJ, CH = PT::CH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto issue = [&](int st) {
         if (st < nst) {
-            double* base = smem + static_cast<size_t>(st % PSTAGES) * ((PM + PN) * PLD);
+            double* base = smem + static_cast<size_t>(st % PSTAGES) * ((PM + TN) * PLD);
             const int k0 = (ks_lo + st) * PK;
 #pragma unroll
             for (int q = 0; q < CH; ++q) {
@@ -231,7 +232,7 @@ __device__ __forceinline__ void path_mainloop(const PathArgs& p, double* smem, i
         cp_async_wait<PSTAGES - 2>();
         __syncthreads();
         issue(s + PSTAGES - 1);
-        const double* tG = smem + static_cast<size_t>(s % PSTAGES) * ((PM + PN) * PLD);
+        const double* tG = smem + static_cast<size_t>(s % PSTAGES) * ((PM + TN) * PLD);
         const double* tY = tG + PM * PLD;
 #pragma unroll
         for (int k4 = 0; k4 < PK; k4 += 4) {
@@ -251,10 +252,12 @@ __device__ __forceinline__ void path_mainloop(const PathArgs& p, double* smem, i
 }
 
 // iblk: index of the tile's i-block (row of the partial-sum arrays)
-template <int PM>
+template <int PM, int TN = PN>
 __device__ __forceinline__ void path_epilogue(const PathArgs& p, int i0, int l0, int iblk,
-                                              double (&acc)[4][PathTile<PM>::NJ][2], double (*part)[PathTile<PM>::LW][4]) {
-    constexpr int WI = PathTile<PM>::WI, WL = PathTile<PM>::WL, LW = PathTile<PM>::LW, NJ = PathTile<PM>::NJ;
+                                              double (&acc)[4][PathTile<PM, TN>::NJ][2],
+                                              double (*part)[PathTile<PM, TN>::LW][4]) {
+    using PT = PathTile<PM, TN>;
+    constexpr int WI = PT::WI, WL = PT::WL, LW = PT::LW, NJ = PT::NJ;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wi = warp / WL, wl = warp % WL;
     const int fk = lane & 3, fc = lane >> 2;
@@ -320,16 +323,18 @@ __device__ __forceinline__ void path_epilogue(const PathArgs& p, int i0, int l0,
                 if (fc == 0) part[warp][j * 8 + fk * 2 + e][q] = v;
             }
     __syncthreads();
-    // combine the WI i-warps of each l, fixed order; 64 l x 4 sums = 256 threads
-    const int l_loc = tid >> 2, q = tid & 3;
-    const int wl2 = l_loc / LW, lw = l_loc % LW;
-    double t = 0.0;
+    // combine the WI i-warps of each l, fixed order; TN l x 4 sums over the 256 threads
+    for (int item = tid; item < TN * 4; item += 256) {
+        const int l_loc = item >> 2, q = item & 3;
+        const int wl2 = l_loc / LW, lw = l_loc % LW;
+        double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < WI; ++w) t += part[w * WL + wl2][lw][q];
-    if (p.mode == 0) {
-        if (q == 0) p.step_part[static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc] = t;
-    } else {
-        p.obj_part[(static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc) * 4 + q] = t;
+        for (int w = 0; w < WI; ++w) t += part[w * WL + wl2][lw][q];
+        if (p.mode == 0) {
+            if (q == 0) p.step_part[static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc] = t;
+        } else {
+            p.obj_part[(static_cast<size_t>(iblk) * p.Lpad + l0 + l_loc) * 4 + q] = t;
+        }
     }
 }
 
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
 // ------------------------------------------------------------------------------------------
 struct PathSkArgs {
     PathArgs p;
-    double* W;            // [P][2][32][256] double: partial accumulators (fragment layout), 2 slots per CTA
+    double* W;            // [P][2][128 x TN] double: partial accumulators (fragment layout), 2 slots per CTA
     unsigned* ticket;     // [T] arrivals per tile (reset by the finishing CTA)
     int T, KT, P;         // tiles, k-steps per tile, CTAs
 };
@@ -363,30 +368,34 @@ __device__ __forceinline__ long long sk_begin(const PathSkArgs& a, int c) {
     return (static_cast<long long>(a.T) * a.KT * c) / a.P;
 }
 
+// TN = 64 or 128 penalties per tile: 128 x 128 tiles (warp tile 32 x 64, 12 fragment loads per 32 MMAs, as in
+// the SYRK kernel) are the efficient shape, and with equal k-step ranges their small number (64 tiles at 256
+// penalties) no longer starves SMs
+template <int TN>
 __global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a) {
     constexpr int PM = 128;
-    constexpr int NJ = PathTile<PM>::NJ;
+    constexpr int NJ = PathTile<PM, TN>::NJ;
     extern __shared__ __align__(16) double smem[];
-    __shared__ double part[8][PathTile<PM>::LW][4];
+    __shared__ double part[8][PathTile<PM, TN>::LW][4];
     __shared__ unsigned s_ticket;
     const PathArgs& p = a.p;
     const int tid = threadIdx.x;
     const int c = blockIdx.x;
-    const int nlb = p.Lpad / PN;                 // l-blocks; tile t = (iblk = t / nlb, lblk = t % nlb)
+    const int nlb = p.Lpad / TN;                 // l-blocks; tile t = (iblk = t / nlb, lblk = t % nlb)
     const long long r0 = sk_begin(a, c), r1 = sk_begin(a, c + 1);
     double acc[4][NJ][2];
     for (long long r = r0; r < r1;) {
         const int t = static_cast<int>(r / a.KT);
         const int k_lo = static_cast<int>(r - static_cast<long long>(t) * a.KT);
         const int k_hi = static_cast<int>(min(static_cast<long long>(a.KT), r1 - static_cast<long long>(t) * a.KT));
-        const int iblk = t / nlb, i0 = iblk * PM, l0 = (t % nlb) * PN;
-        path_mainloop<PM>(p, smem, i0, l0, k_lo, k_hi - k_lo, acc);
+        const int iblk = t / nlb, i0 = iblk * PM, l0 = (t % nlb) * TN;
+        path_mainloop<PM, TN>(p, smem, i0, l0, k_lo, k_hi - k_lo, acc);
         if (k_lo == 0 && k_hi == a.KT) {
-            path_epilogue<PM>(p, i0, l0, iblk, acc, part);
+            path_epilogue<PM, TN>(p, i0, l0, iblk, acc, part);
         } else {
             // publish the partial (slot = 0 for a range that starts inside a tile, 1 for the one that ends inside)
             const int slot = (k_lo != 0) ? 0 : 1;
-            double2* w = reinterpret_cast<double2*>(a.W + (static_cast<size_t>(c) * 2 + slot) * (PM * PN));
+            double2* w = reinterpret_cast<double2*>(a.W + (static_cast<size_t>(c) * 2 + slot) * (PM * TN));
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a
                     // slot 0: the contributor's range STARTS inside this tile; slot 1: it starts at or before the
                     // tile's first k-step (and ends inside it) -- the rule the contributors used above
                     const int slot_cc = (sk_begin(a, cc) > tb) ? 0 : 1;
-                    const double2* wv = reinterpret_cast<const double2*>(a.W + (static_cast<size_t>(cc) * 2 + slot_cc) * (PM * PN));
+                    const double2* wv = reinterpret_cast<const double2*>(a.W + (static_cast<size_t>(cc) * 2 + slot_cc) * (PM * TN));
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a
                         }
                 }
                 if (tid == 0) a.ticket[t] = 0u;   // ready for the next launch
-                path_epilogue<PM>(p, i0, l0, iblk, acc, part);
+                path_epilogue<PM, TN>(p, i0, l0, iblk, acc, part);
             }
             __syncthreads();
         }
@@ -1057,11 +1066,12 @@ static cudaError_t launch_path(const PathArgs& p, cudaStream_t st) {
 }
 
 // stream-K launch (128 x 64 tiles only); W and ticket are owned by the caller
+template <int TN>
 static cudaError_t launch_path_sk(const PathArgs& p, double* W, unsigned* ticket, int P, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(PSTAGES) * (128 + PN) * PLD * sizeof(double);
+    const size_t smem = static_cast<size_t>(PSTAGES) * (128 + TN) * PLD * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -1070,10 +1080,10 @@ static cudaError_t launch_path_sk(const PathArgs& p, double* W, unsigned* ticket
     a.p = p;
     a.W = W;
     a.ticket = ticket;
-    a.T = (p.d / 128) * (p.Lpad / PN);
+    a.T = (p.d / 128) * (p.Lpad / TN);
     a.KT = p.d / PK;
     a.P = P;
-    path_step_sk_kernel<<<dim3(P), dim3(256), smem, st>>>(a);
+    path_step_sk_kernel<TN><<<dim3(P), dim3(256), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1100,6 +1110,9 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
     const long long tiles128 = static_cast<long long>(d / 128) * (Lpad / PN);
     bool use_sk = d % 128 == 0 && tiles128 * (d / PK) >= 4LL * sm_count && tiles128 <= 4LL * sm_count;
     if (const char* e = getenv("FOS_PATH_SK")) use_sk = use_sk && e[0] != '0';
+    // 128-penalty tiles when that costs no extra padding (FOS_PATH_TN=64 forces the narrow tile)
+    int tn = (use_sk && Lpad % 128 == 0) ? 128 : PN;
+    if (const char* e = getenv("FOS_PATH_TN")) tn = (atoi(e) == 128 && use_sk && Lpad % 128 == 0) ? 128 : PN;
     if (use_sk) pm = 128;
     const int nblk = d / pm;
     const size_t mat = static_cast<size_t>(Lpad) * d;
@@ -1125,7 +1138,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&smax), sizeof(double)));
         FOS_CUDA(fos_pool_malloc_host(reinterpret_cast<void**>(&smax_host), sizeof(double)));
         if (use_sk) {
-            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&skW), static_cast<size_t>(sm_count) * 2 * 128 * PN * sizeof(double)));
+            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&skW), static_cast<size_t>(sm_count) * 2 * 128 * tn * sizeof(double)));
             FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&sk_ticket), static_cast<size_t>(tiles128) * sizeof(unsigned)));
             FOS_CUDA(cudaMemsetAsync(sk_ticket, 0, static_cast<size_t>(tiles128) * sizeof(unsigned), g->stream));
         }
@@ -1166,7 +1179,9 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
             p.Yout = (k & 1) ? Y0 : Y1;
             const bool check = pp->tol > 0.0 && ((k + 1) % pp->check_every == 0);
             p.step_part = check ? spart : nullptr;
-            FOS_CUDA(use_sk ? launch_path_sk(p, skW, sk_ticket, sm_count, g->stream) : launch_path_pm(pm, p, g->stream));
+            FOS_CUDA(!use_sk ? launch_path_pm(pm, p, g->stream)
+                             : (tn == 128 ? launch_path_sk<128>(p, skW, sk_ticket, sm_count, g->stream)
+                                          : launch_path_sk<PN>(p, skW, sk_ticket, sm_count, g->stream)));
             ++n_launch;
             ++iters;
             if (check) {
@@ -1184,7 +1199,9 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         p.Yin = X;
         p.Yout = nullptr;
         p.step_part = nullptr;
-        FOS_CUDA(use_sk ? launch_path_sk(p, skW, sk_ticket, sm_count, g->stream) : launch_path_pm(pm, p, g->stream));
+        FOS_CUDA(!use_sk ? launch_path_pm(pm, p, g->stream)
+                             : (tn == 128 ? launch_path_sk<128>(p, skW, sk_ticket, sm_count, g->stream)
+                                          : launch_path_sk<PN>(p, skW, sk_ticket, sm_count, g->stream)));
         path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, nblk, Lpad, a1, pp->alpha2,
                                                                                    0.5 * g->bb, obj);
         n_launch += 2;
