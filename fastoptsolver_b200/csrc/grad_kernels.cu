@@ -36,12 +36,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 2;" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -95,9 +89,6 @@ struct Vec<float> {
 
 
 constexpr int MAX_STAGES = 8;
-#ifndef FOS_SKEW_DEFAULT
-#define FOS_SKEW_DEFAULT false
-#endif
 
 // ------------------------------------------------------------------------------------------
 // streaming kernel
@@ -108,7 +99,6 @@ constexpr int MAX_STAGES = 8;
 template <int NW, int R>
 struct StreamSmem {
     uint64_t full_bar[MAX_STAGES];
-    uint64_t red_bar[2];      // split-phase barrier of the cross-warp exchange, one per parity buffer
     double red[2][R][NW][2];  // [parity][row][warp][dot1, dot2]
 };
 
@@ -333,283 +323,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Skewed consumer loop (software pipelined across stages).  Same arithmetic on the same operands
-// in the same order as stream_consume -- bit-identical results -- but the per-stage dependency
-// chain  wait -> LDS -> dot FMAs -> butterfly -> exchange -> tree -> rank-1 update  is cut in two:
-// while stage s goes through its reduction (SHFL butterfly, shared-memory exchange), the loads and
-// dot products of stage s+1 are already in flight in a second register set.  The cross-warp
-// exchange uses a split-phase mbarrier (writers arrive right after their store, everybody waits
-// only just before reading), so a warp never waits for the slowest warp to reach the same program
-// point, only for its store.  With 2 warps per scheduler this is the latency hiding the plain loop
-// lacks (ncu: 6.9 cycles per issued instruction, short_scoreboard + wait + barrier = 4.1 of them).
-// ------------------------------------------------------------------------------------------
-template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2>
-__device__ __forceinline__ void stream_consume_skew(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
-                                                    unsigned char* ring, int stage_bytes, int nstage,
-                                                    long long lo, long long hi, bool use_b, uint64_t pol, int cta) {
-    constexpr int VEC = Vec<T>::N;
-    constexpr int NV = CPT / VEC;
-    constexpr int NW = NT / 32;
-    constexpr int NCH = (CPT >= 16) ? 4 : 2;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t row_bytes = static_cast<uint32_t>(a.lda) * sizeof(T);
-    const int nst = static_cast<int>((hi - lo + R - 1) / R);
-    if (nst <= 0) {
-        // no rows for this CTA: publish zero partials
-        if (GRAD) {
-            double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
-            for (int c = 2 * tid; c < a.ldv; c += 2 * NT) *reinterpret_cast<double2*>(out + c) = make_double2(0.0, 0.0);
-        }
-        if (tid == 0) a.partial_s[2 * cta + 0] = a.partial_s[2 * cta + 1] = 0.0;
-        return;
-    }
-
-    double v1[NV][VEC], v2[NV][VEC], acc[NV][VEC];
-    uint32_t off[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c0 = VEC * (tid + NT * j);
-        off[j] = (c0 < a.lda) ? static_cast<uint32_t>(c0) * sizeof(T) : 0u;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const int c = c0 + e;
-            v1[j][e] = (GRAD && c < a.d) ? a.v1[c] : 0.0;
-            v2[j][e] = (DOT2 && c < a.d) ? a.v2[c] : 0.0;
-            acc[j][e] = 0.0;
-        }
-    }
-    double s1 = 0.0, s2 = 0.0;
-
-    const int blane = lane & 15;
-    const bool b_lane = use_b && warp == 0 && blane < R;
-    const double* bp = a.b + lo + blane;
-    long long b_left = hi - lo - blane;
-    double b_cur = 0.0, b_nxt = 0.0;
-    if (b_lane && b_left > 0) b_cur = __ldg(bp);
-    if (b_lane && b_left > R) b_nxt = __ldg(bp + R);
-
-    const uint32_t ring_u32 = smem_u32(ring);
-    const bool upper = (lane & 16) != 0;
-    const bool sums_here = (warp == 0);
-
-    // ---- pieces of one stage
-    auto load_stage = [&](double (&av)[R][NV][VEC], int slot, int rows) {
-        const uint32_t st = ring_u32 + static_cast<uint32_t>(slot) * static_cast<uint32_t>(stage_bytes);
-        if (rows == R) {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int j = 0; j < NV; ++j) Vec<T>::load_shared(st + r * row_bytes + off[j], av[r][j]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    if (r < rows) {
-                        Vec<T>::load_shared(st + r * row_bytes + off[j], av[r][j]);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) av[r][j][e] = 0.0;
-                    }
-                }
-        }
-    };
-    auto dots = [&](const double (&av)[R][NV][VEC], double (&d1)[R], double (&d2)[R]) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double p1[NCH], p2[NCH];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) p1[c] = p2[c] = 0.0;
-#pragma unroll
-            for (int j = 0; j < NV; ++j)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const int c = (j * VEC + e) % NCH;
-                    if (GRAD) p1[c] = fma(av[r][j][e], v1[j][e], p1[c]);
-                    if (DOT2) p2[c] = fma(av[r][j][e], v2[j][e], p2[c]);
-                }
-            if (NCH == 4) {
-                d1[r] = GRAD ? (p1[0] + p1[1]) + (p1[2] + p1[3]) : 0.0;
-                d2[r] = DOT2 ? (p2[0] + p2[1]) + (p2[2] + p2[3]) : 0.0;
-            } else {
-                d1[r] = GRAD ? p1[0] + p1[1] : 0.0;
-                d2[r] = DOT2 ? p2[0] + p2[1] : 0.0;
-            }
-        }
-    };
-    // warp reduction of the per-thread dots, store of the warp partials, arrival on the exchange barrier
-    auto reduce_publish = [&](double (&d1)[R], double (&d2)[R], int par) {
-        if (GRAD && DOT2) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const double keep = upper ? d2[r] : d1[r];
-                const double send = upper ? d1[r] : d2[r];
-                double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (blane == r) {
-                    const double bi = (warp == 0) ? b_cur : 0.0;
-                    sm.red[par][r][warp][upper ? 1 : 0] = v - bi;
-                    mbar_arrive(&sm.red_bar[par]);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (GRAD) d1[r] = fos_warp_sum(d1[r]);
-                if (DOT2) d2[r] = fos_warp_sum(d2[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (lane == r) {
-                    const double bi = (warp == 0) ? b_cur : 0.0;
-                    *reinterpret_cast<double2*>(&sm.red[par][r][warp][0]) =
-                        make_double2(GRAD ? d1[r] - bi : 0.0, DOT2 ? d2[r] - bi : 0.0);
-                    mbar_arrive2(&sm.red_bar[par]);  // the barrier counts two arrivals per (warp, row)
-                }
-            }
-        }
-    };
-    // ordered sum over the warp partials, rank-1 update with the row held in registers
-    auto finish_stage = [&](const double (&av)[R][NV][VEC], int par, int rows) {
-        double r1[R], r2[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double2 pr[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) pr[w] = *reinterpret_cast<const double2*>(&sm.red[par][r][w][0]);
-#pragma unroll
-            for (int span = 1; span < NW; span *= 2)
-#pragma unroll
-                for (int w = 0; w + span < NW; w += 2 * span) {
-                    if (GRAD) pr[w].x += pr[w + span].x;
-                    if (DOT2 && sums_here) pr[w].y += pr[w + span].y;
-                }
-            r1[r] = pr[0].x;
-            r2[r] = pr[0].y;
-        }
-        if (GRAD) {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int j = 0; j < NV; ++j)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[j][e] = fma(r1[r], av[r][j][e], acc[j][e]);
-        }
-        if (sums_here) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r < rows) {
-                    if (GRAD) s1 = fma(r1[r], r1[r], s1);
-                    if (DOT2) s2 = fma(r2[r], r2[r], s2);
-                }
-            }
-        }
-    };
-
-    // ring position of the stage being LOADED next
-    int slot_n = 0;
-    uint32_t par_n = 0;
-    auto advance_load = [&]() {
-        if (++slot_n == nstage) {
-            slot_n = 0;
-            par_n ^= 1u;
-        }
-    };
-    auto rows_of = [&](int s) {
-        return static_cast<int>(min(static_cast<long long>(R), hi - lo - static_cast<long long>(s) * R));
-    };
-
-    // One step: stage s sits in `cur` with its per-thread dots in (dc1, dc2); stage s+1 is loaded
-    // into `nxt` and its dots formed while stage s is reduced.  STEADY: s+1 exists and is a full stage.
-    int slot_c = 0;  // ring slot of stage s (refilled once everybody has consumed it)
-    auto step = [&](auto steady, double (&cur)[R][NV][VEC], double (&nxt)[R][NV][VEC], double (&dc1)[R],
-                    double (&dc2)[R], double (&dn1)[R], double (&dn2)[R], int s) {
-        constexpr bool STEADY = decltype(steady)::value;
-        double b_far = 0.0;
-        if (b_lane && b_left > 2 * R) b_far = __ldg(bp + 2 * R);
-        bp += R;
-        b_left -= R;
-        const bool has_next = STEADY || (s + 1 < nst);
-        const int par = s & 1;
-        const int slot_next = slot_n;
-        if (has_next) {
-            mbar_wait(&sm.full_bar[slot_n], par_n);
-            load_stage(nxt, slot_n, STEADY ? R : rows_of(s + 1));
-            advance_load();
-        }
-        reduce_publish(dc1, dc2, par);
-        if (has_next) {
-            dots(nxt, dn1, dn2);
-            // pin the dot products of stage s+1 ABOVE the wait below (the compiler otherwise sinks
-            // them past it): they are the work that covers the other warps' way to their arrivals
-#pragma unroll
-            for (int r = 0; r < R; ++r) asm volatile("" ::"d"(dn1[r]), "d"(dn2[r]));
-        }
-        // everybody's partials of stage s are in shared memory; everybody has also consumed the ring
-        // slot of stage s (its dots were formed before these arrivals): thread 0 refills it
-        mbar_wait(&sm.red_bar[par], static_cast<uint32_t>(s >> 1) & 1u);
-        if (tid == 0 && s + nstage < nst) {
-            const long long rs = lo + static_cast<long long>(s + nstage) * R;
-            const int nr = static_cast<int>(min(static_cast<long long>(R), hi - rs));
-            const uint32_t bytes = static_cast<uint32_t>(nr) * row_bytes;
-            mbar_expect_tx(&sm.full_bar[slot_c], bytes);
-            bulk_g2s(ring + static_cast<size_t>(slot_c) * stage_bytes,
-                     static_cast<const unsigned char*>(a.A) + static_cast<size_t>(rs) * row_bytes, bytes,
-                     &sm.full_bar[slot_c], pol);
-        }
-        finish_stage(cur, par, STEADY ? R : rows_of(s));
-        b_cur = b_nxt;
-        b_nxt = b_far;
-        slot_c = slot_next;
-    };
-
-    double avA[R][NV][VEC], avB[R][NV][VEC];
-    double dA1[R], dA2[R], dB1[R], dB2[R];
-    // prologue: stage 0
-    mbar_wait(&sm.full_bar[0], 0);
-    load_stage(avA, 0, rows_of(0));
-    advance_load();
-    dots(avA, dA1, dA2);
-    slot_c = 0;
-
-    using Steady = std::integral_constant<bool, true>;
-    using Tail = std::integral_constant<bool, false>;
-    int s = 0;
-    for (; s + 3 < nst; s += 2) {  // both steps load a full stage: s+1 and s+2 are < nst-1
-        step(Steady{}, avA, avB, dA1, dA2, dB1, dB2, s);
-        step(Steady{}, avB, avA, dB1, dB2, dA1, dA2, s + 1);
-    }
-    if (s < nst) step(Tail{}, avA, avB, dA1, dA2, dB1, dB2, s++);
-    if (s < nst) step(Tail{}, avB, avA, dB1, dB2, dA1, dA2, s++);
-    if (s < nst) step(Tail{}, avA, avB, dA1, dA2, dB1, dB2, s++);
-
-    if (GRAD) {
-        double* out = a.partial_g + static_cast<size_t>(cta) * a.ldv;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c0 = VEC * (tid + NT * j);
-#pragma unroll
-            for (int e = 0; e < VEC; e += 2)
-                if (c0 + e < a.ldv) *reinterpret_cast<double2*>(out + c0 + e) = make_double2(acc[j][e], acc[j][e + 1]);
-        }
-    }
-    if (tid == 0) {
-        a.partial_s[2 * cta + 0] = s1;
-        a.partial_s[2 * cta + 1] = s2;
-        if (a.cta_times) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            a.cta_times[2 * cta + 1] = (fos_globaltimer() & 0xFFFFFFFFFFFFull) | (static_cast<unsigned long long>(smid) << 48);
-        }
-    }
-}
-
 // LITE: gradient-only build (modes GM_GRAD [| GM_NOB]); used for wide rows (d > 4096) by the loops
 // that never need the second dot (L-BFGS, power iteration, fos_grad), where dropping v2 lets 256
 // threads own 32 columns each -- half the per-element reduction cost of the 512-thread build.
-template <typename T, int NT, int CPT, int R, bool LITE = false, bool SKEW = false>
+template <typename T, int NT, int CPT, int R, bool LITE = false>
 __global__ void __launch_bounds__(NT, 1)
 grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     constexpr int NW = NT / 32;
@@ -643,10 +360,6 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         const long long lo0 = a.row_lo[cta0], hi0 = a.row_lo[cta0 + 1];
         const int nst0 = static_cast<int>((hi0 - lo0 + R - 1) / R);
         for (int s = 0; s < nstage; ++s) mbar_init(&sm.full_bar[s], 1);
-        // exchange barrier of the skewed loop: one arrival per (warp, row) partial store; with both
-        // dots the two half-warps store (and arrive) separately
-        mbar_init(&sm.red_bar[0], NW * R * 2);
-        mbar_init(&sm.red_bar[1], NW * R * 2);
         mbar_fence_init();
         // prologue: fill the ring (thread 0 is also the only thread that refills it later)
         pol = l2_evict_first_policy();
@@ -711,30 +424,18 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     int slot0 = 0;
     uint32_t par0 = 0;
     if (LITE) {
-        if constexpr (SKEW)
-            stream_consume_skew<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
-        else
-            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
+        stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
         return;
     }
     switch (mode & (GM_GRAD | GM_DOT2)) {
         case GM_GRAD:
-            if constexpr (SKEW)
-                stream_consume_skew<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
-            else
-                stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
+            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
         case GM_DOT2:
-            if constexpr (SKEW)
-                stream_consume_skew<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
-            else
-                stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
+            stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
         default:
-            if constexpr (SKEW)
-                stream_consume_skew<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta);
-            else
-                stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
+            stream_consume<T, NT, CPT, R, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
     }
 }
@@ -871,8 +572,6 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
         const long long lo0 = a.row_lo[cta0], hi0 = a.row_lo[cta0 + 1];
         const int nst0 = static_cast<int>((hi0 - lo0 + R - 1) / R);
         for (int s = 0; s < nstage; ++s) mbar_init(&sm.full_bar[s], 1);
-        mbar_init(&sm.red_bar[0], NW * R * 2);
-        mbar_init(&sm.red_bar[1], NW * R * 2);
         mbar_fence_init();
         pol = l2_evict_first_policy();
         const size_t row_bytes = static_cast<size_t>(a.lda) * sizeof(T);
@@ -1332,20 +1031,10 @@ struct StreamCfg {
     const void* solve_fn = nullptr;  // persistent solve kernel of the same shape (full-mode builds only)
 };
 
-// FOS_SKEW=1/0: the software-pipelined consumer loop (stream_consume_skew) or the plain one
-bool use_skew() {
-    static const bool on = [] {
-        const char* e = getenv("FOS_SKEW");
-        return e ? e[0] == '1' : FOS_SKEW_DEFAULT;
-    }();
-    return on;
-}
-
 template <typename T, int NT, int CPT, int R, bool LITE = false>
 StreamCfg make_cfg() {
     StreamCfg c;
-    c.fn = use_skew() ? reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, true>)
-                      : reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE, false>);
+    c.fn = reinterpret_cast<const void*>(&grad_stream_kernel<T, NT, CPT, R, LITE>);
     c.nt = NT;
     c.cpt = CPT;
     c.r = R;

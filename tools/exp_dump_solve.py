@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Run one FISTA solve (fixed step and Armijo, with history) plus a power iteration on a synthetic
 design and dump every output to an .npz -- for A/B comparisons of library builds / switches
-(FOS_SKEW, FOS_LIB_PATH, ...) that must leave the results bit-identical.
+(FOS_FUSED, FOS_LIB_PATH, ...) that must leave the results bit-identical.
 
-    FOS_SKEW=0 python tools/exp_dump_solve.py out0.npz ; FOS_SKEW=1 python tools/exp_dump_solve.py out1.npz
+    FOS_FUSED=0 python tools/exp_dump_solve.py out0.npz ; FOS_FUSED=1 python tools/exp_dump_solve.py out1.npz
     python tools/exp_dump_solve.py --compare out0.npz out1.npz
 """
 import os
