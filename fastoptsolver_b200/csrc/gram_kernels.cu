@@ -591,6 +591,9 @@ struct fos_gram {
 static void gram_free(fos_gram* g) {
     if (!g) return;
     cudaSetDevice(g->device);
+    // recycled blocks are handed to the next request without the implicit device synchronisation of cudaFree:
+    // nothing of this object may still be running
+    if (g->stream) cudaStreamSynchronize(g->stream);
     fos_pool_free(g->G);
     fos_pool_free(g->c);
     if (g->ev0) cudaEventDestroy(g->ev0);
@@ -766,6 +769,7 @@ int fos_upload_gram_finish(fos_design* h, cudaStream_t s) {
 }
 
 void fos_upload_gram_drop(fos_design* h) {
+    if (h->G_up || h->up_W) cudaDeviceSynchronize();  // recycled blocks: no kernel may still read them (rare path)
     if (h->up_W) ws_give(h->device, h->up_W, h->up_W_bytes);
     fos_pool_free(h->G_up);
     h->up_W = nullptr;
@@ -1041,6 +1045,7 @@ extern "C" int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* 
         return FOS_OK;
     };
     const int st = body();
+    if (st != FOS_OK) cudaStreamSynchronize(g->stream);
     fos_pool_free(buf);
     return st;
 }
@@ -1218,6 +1223,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         return FOS_OK;
     };
     const int st = body();
+    if (st != FOS_OK) cudaStreamSynchronize(g->stream);
     cleanup();
     return st;
 }
