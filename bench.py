@@ -617,8 +617,12 @@ def bench_fista(ctx, cfg_name):
 
     # ---- end-to-end through the public drop-in API on host buffers (rank-local shard)
     if not args.no_e2e:
-        out["e2e"] = e2e_fista(ctx, des, alpha1, K)
-        if world == 1:
+        try:
+            out["e2e"] = e2e_fista(ctx, des, alpha1, K)
+        except (MemoryError, RuntimeError) as e:     # e.g. no room for the pinned host copy: keep the line, say why
+            out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                          "error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and out["e2e"].get("value") is not None:
             # the same call on PAGEABLE arrays (what a numpy caller of the reference passes): the upload
             # then goes through the threaded pinned-staging copy instead of a direct DMA.  Extra
             # information only: a host too small for a second copy of A must not cost the line.
@@ -631,22 +635,31 @@ def bench_fista(ctx, cfg_name):
 
     # ---- CPU baseline on rank 0, N == 1 only
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores, want = use_all_host_threads()
-        A_s, b_s = des.download(0, rows_s)
-        steps_cpu = min(K, 20)
-        res = cpu_fista_run(A_s, b_s, alpha1 * rows_s / n, steps_cpu, n / rows_s)
-        out["cpu_baseline"] = {
-            "value": res["loop_it_s"], "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle.fista on rows [0,{rows_s}) of the same design ({rows_s}x{d} fp64, "
-                      f"{rows_s * d * 8 / 1e9:.2f} GB), {steps_cpu} iterations with history; loop proper "
-                      f"{res['loop_s']:.2f} s (value), Lipschitz estimate {res['lipschitz_s']:.2f} s apart, "
-                      f"whole call {res['wall_s']:.2f} s; rates divided by {n / rows_s:.2f} (rows ratio)",
-            "whole_call_it_s": res["call_it_s"], "gradient_only_it_s": res["grad_it_s"],
-            "lipschitz_s": res["lipschitz_s"], "affinity_cores": want,
-        }
+        try:
+            out["cpu_baseline"] = cpu_fista_record(des, alpha1, rows_s, n, d, K)
+        except Exception as e:            # the CPU sample must not cost the GPU line
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                                   "error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         emit(out)
     ctx.finish(des)
+
+
+def cpu_fista_record(des, alpha1, rows_s, n, d, K):
+    """cpu_baseline of the FISTA configs: the oracle on rows [0, rows_s) of the same design, all host threads."""
+    cores, want = use_all_host_threads()
+    A_s, b_s = des.download(0, rows_s)
+    steps_cpu = min(K, 20)
+    res = cpu_fista_run(A_s, b_s, alpha1 * rows_s / n, steps_cpu, n / rows_s)
+    return {
+        "value": res["loop_it_s"], "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"oracle.fista on rows [0,{rows_s}) of the same design ({rows_s}x{d} fp64, "
+                  f"{rows_s * d * 8 / 1e9:.2f} GB), {steps_cpu} iterations with history; loop proper "
+                  f"{res['loop_s']:.2f} s (value), Lipschitz estimate {res['lipschitz_s']:.2f} s apart, "
+                  f"whole call {res['wall_s']:.2f} s; rates divided by {n / rows_s:.2f} (rows ratio)",
+        "whole_call_it_s": res["call_it_s"], "gradient_only_it_s": res["grad_it_s"],
+        "lipschitz_s": res["lipschitz_s"], "affinity_cores": want,
+    }
 
 
 def fista_config(n, d, gpus, rows_s):
