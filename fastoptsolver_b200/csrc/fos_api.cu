@@ -467,7 +467,7 @@ static void design_free(fos_design* h) {
     const auto f2 = now();
     fos_upload_gram_drop(h);
     const auto f3 = now();
-    void* bufs[] = {h->work_block, h->sm_slot, h->arena};
+    void* bufs[] = {h->work_block, h->sm_slot, h->arena, h->qres};
     for (void* p : bufs) fos_pool_free(p);
     const auto f4 = now();
     fos_pool_free(h->pin_block);
@@ -1388,8 +1388,20 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     c->restart_thr = p->restart_threshold;
     c->delta = p->delta;
     c->armijo_c = p->armijo_c;
+    // Fixed-step solves with history on streaming designs: the recorded objective's residual norm comes from
+    // the row-wise residual recurrence (GM_QREC) instead of a second dot product in every pass (FOS_QREC=0: off)
+    bool qrec = want_obj && !p->backtracking && h->kern_kind == 1 && K > 0;
+    if (const char* e = getenv("FOS_QREC")) qrec = qrec && e[0] != '0';
+    if (qrec && h->qres == nullptr &&
+        fos_pool_malloc(reinterpret_cast<void**>(&h->qres), static_cast<size_t>(h->n) * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        h->qres = nullptr;
+        qrec = false;
+    }
+    c->use_qrec = qrec ? 1 : 0;
+    c->beta_y = 0.0;   // y_0 = x_0
     c->phase = (K > 0) ? PH_GRAD : PH_DONE;
-    c->g_mode = (K > 0) ? GM_GRAD : GM_SKIP;
+    c->g_mode = (K > 0) ? (GM_GRAD | (qrec ? GM_QREC : 0)) : GM_SKIP;
     c->tau = p->step0;
     c->trial_t = p->step0;
     c->t_mom = 1.0;

@@ -50,6 +50,8 @@ enum : int {
     GM_DOT2 = 2,  // r2 = A v2 - b ; s2 += r2^2
     GM_NOB = 4,   // treat b as zero (power iteration)
     GM_PROBE = 8, // diagnostic: run the bulk-copy ring only, consumers discard the data
+    GM_QREC = 16, // with GM_GRAD: s2 = |A x_k - b|^2 from the residual recurrence instead of a second dot:
+                  // y_k = x_k + beta (x_k - x_{k-1})  =>  A x_k - b = (r_y + beta q_{k-1}) / (1 + beta), q stored per row
 };
 
 // phases of the proximal-gradient state machine (FosCtrl::phase)
@@ -88,6 +90,8 @@ struct FosCtrl {
     unsigned long long epi_ns, xchg_ns;  // accumulated epilogue time / time spent waiting for peers
     unsigned long long grad_ns;          // persistent solve kernel: accumulated time from the start of a pass until
                                          // every CTA has published its partials (the gradient phase proper)
+    int use_qrec, pad_q;                 // the recorded objective comes from the residual recurrence (GM_QREC)
+    double beta_y;                       // momentum coefficient the current y was formed with (0: y == x)
     // ---- power iteration
     double L, L_prev, ptol;
     int pit, pit_max;
@@ -155,6 +159,7 @@ struct GradArgs {
     unsigned* slot_claim;           // [n_parts] pass number that last claimed each slot (with sm_slot)
     unsigned pass_no;               // number of this launch (monotonic per design): the claim token
     unsigned long long* cta_times;  // debug: [n_parts][2] start/end %globaltimer per CTA (nullable)
+    double* qres;                   // [n] residual A x_k - b of the current iterate, row by row (GM_QREC; nullable)
 };
 
 // Everything the epilogue kernel needs.
@@ -219,6 +224,7 @@ struct fos_design {
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
     FosGridSync* gsync = nullptr;  // persistent solve kernel (streaming designs only)
+    double* qres = nullptr;        // [n] residual vector of the recurrence (allocated by the first solve that uses it)
     bool fused_ok = false;         // the whole solve may run as ONE launch of the persistent kernel
     bool lite_ok = false;         // a gradient-only kernel variant exists for this shape
     bool grad_only_hint = false;  // the running loop never asks for the second dot

@@ -110,11 +110,16 @@ struct StreamSmem {
 // same rows (A never changes), so HBM keeps streaming while the pass's tail runs; slot_io / parity_io
 // carry the ring position from pass to pass, and the vectors are read through L2 (other CTAs of the
 // same launch wrote them).  Requires nst >= nstage.
-template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2, bool WRAP = false>
+// QREC (with GRAD, without DOT2): the second residual norm s2 = |A x_k - b|^2 comes from the recurrence
+//   q_k = (r_y + beta q_{k-1}) / (1 + beta),  r_y = A y_k - b,  y_k = x_k + beta (x_k - x_{k-1})
+// kept row by row in a.qres (16 bytes of traffic per row instead of 16 FMAs per 16 elements: the pass is 10 %
+// faster on a power-capped part).  Warp 0 carries it: q_{k-1} of the stage's rows is requested at the top of
+// the stage and consumed after the ordered sum, one FMA + one multiply per row.
+template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2, bool WRAP = false, bool QREC = false>
 __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
                                                unsigned char* ring, int stage_bytes, int nstage,
                                                long long lo, long long hi, bool use_b, uint64_t pol, int cta,
-                                               int& slot_io, uint32_t& parity_io) {
+                                               int& slot_io, uint32_t& parity_io, double beta_y = 0.0) {
     constexpr int VEC = Vec<T>::N;
     constexpr int NV = CPT / VEC;
     constexpr int NW = NT / 32;
@@ -137,6 +142,7 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         }
     }
     double s1 = 0.0, s2 = 0.0;
+    const double q_inv = QREC ? 1.0 / (1.0 + beta_y) : 1.0;
 
     // b values of the next two stages, prefetched by lanes < R of both half-warps of warp 0 (each
     // half subtracts b from the dot it ends up holding, see the paired butterfly below)
@@ -158,6 +164,12 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         b_left -= R;
         const int rows = static_cast<int>(min(static_cast<long long>(R), hi - lo - static_cast<long long>(s) * R));
         const uint32_t st = ring_u32 + static_cast<uint32_t>(slot) * static_cast<uint32_t>(stage_bytes);
+        double q_old[R];
+        if (QREC && warp == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                q_old[r] = (beta_y != 0.0 && r < rows) ? __ldcg(a.qres + lo + static_cast<long long>(s) * R + r) : 0.0;
+        }
 
         mbar_wait(&sm.full_bar[slot], parity);
 
@@ -288,6 +300,11 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 if (r < rows) {
                     if (GRAD) s1 = fma(r1[r], r1[r], s1);
                     if (DOT2) s2 = fma(r2[r], r2[r], s2);
+                    if (QREC) {
+                        const double qn = fma(beta_y, q_old[r], r1[r]) * q_inv;
+                        s2 = fma(qn, qn, s2);
+                        if (lane == 0) a.qres[lo + static_cast<long long>(s) * R + r] = qn;
+                    }
                 }
             }
         }
@@ -429,7 +446,11 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
     }
     switch (mode & (GM_GRAD | GM_DOT2)) {
         case GM_GRAD:
-            stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
+            if ((mode & GM_QREC) && a.qres != nullptr)
+                stream_consume<T, NT, CPT, R, true, false, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol,
+                                                                        cta, slot0, par0, a.ctrl->beta_y);
+            else
+                stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
         case GM_DOT2:
             stream_consume<T, NT, CPT, R, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
@@ -637,7 +658,11 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
         } else {
             switch (mode & (GM_GRAD | GM_DOT2)) {
                 case GM_GRAD:
-                    stream_consume<T, NT, CPT, R, true, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
+                    if ((mode & GM_QREC) && a.qres != nullptr)
+                        stream_consume<T, NT, CPT, R, true, false, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol,
+                                                                               cta, slot, parity, ts.ctrl.beta_y);
+                    else
+                        stream_consume<T, NT, CPT, R, true, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
                     break;
                 case GM_DOT2:
                     stream_consume<T, NT, CPT, R, false, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
@@ -1203,6 +1228,7 @@ int fos_launch_solve(fos_design* h, const FosHist& hist, long long max_passes) {
     a.ldv = h->ldv;
     a.mode_override = -1;
     a.cta_times = nullptr;
+    a.qres = h->qres;
     a.row_lo = h->row_lo;
     a.sm_slot = h->sm_slot;
     a.slot_claim = a.sm_slot ? reinterpret_cast<unsigned*>(h->sm_slot + 256) : nullptr;
@@ -1249,6 +1275,7 @@ int fos_launch_grad(fos_design* h, int mode_override) {
     a.ldv = h->ldv;
     a.mode_override = mode_override;
     a.cta_times = h->cta_times;
+    a.qres = h->qres;
     a.row_lo = h->row_lo;
     a.sm_slot = (h->kern_kind == 1) ? h->sm_slot : nullptr;
     a.slot_claim = a.sm_slot ? reinterpret_cast<unsigned*>(h->sm_slot + 256) : nullptr;

@@ -31,7 +31,8 @@ __device__ __forceinline__ double pg_prox_point(double y, double t, double g, do
 // snapshot of the control block taken at the start of a pass's epilogue
 struct PgIn {
     int phase, scheme, backtracking, adaptive_restart, k, obj_pending, want_obj, obj_terms, shrinks, n_grad_calls;
-    int max_iter, stop_reason;
+    int max_iter, stop_reason, use_qrec;
+    double beta_y;
     double a1, a2, tau, trial_t, gy, gd, cand_xx, pend_l2, pend_l1, t_mom, prev_step;
     double eta, armijo_c, tol, tol_ratio, restart_thr, delta;
     unsigned long long pass_t0;
@@ -51,6 +52,7 @@ __device__ __forceinline__ PgIn pg_read(const FosCtrl* C) {
         in.t_mom = V->t_mom; in.prev_step = V->prev_step; in.eta = V->eta; in.armijo_c = V->armijo_c;
         in.tol = V->tol; in.tol_ratio = V->tol_ratio; in.restart_thr = V->restart_thr; in.delta = V->delta;
         in.pass_t0 = V->pass_t0;
+        in.use_qrec = V->use_qrec; in.beta_y = V->beta_y;
     } else {
         in.phase = C->phase; in.scheme = C->scheme; in.backtracking = C->backtracking;
         in.adaptive_restart = C->adaptive_restart; in.k = C->k; in.obj_pending = C->obj_pending;
@@ -61,6 +63,7 @@ __device__ __forceinline__ PgIn pg_read(const FosCtrl* C) {
         in.t_mom = C->t_mom; in.prev_step = C->prev_step; in.eta = C->eta; in.armijo_c = C->armijo_c;
         in.tol = C->tol; in.tol_ratio = C->tol_ratio; in.restart_thr = C->restart_thr; in.delta = C->delta;
         in.pass_t0 = C->pass_t0;
+        in.use_qrec = C->use_qrec; in.beta_y = C->beta_y;
     }
     return in;
 }
@@ -133,7 +136,7 @@ __device__ __forceinline__ void pg_elem1_trial(const EpiArgs& e, const PgIn& in,
 // everything the scalar logic decides (identical in every thread that runs it)
 struct PgOut {
     int n_phase, n_gmode, n_k, n_shrinks, n_obj_pending, n_stop, n_ngrad;
-    double n_tau, n_trial, n_gy, n_gd, n_cxx, n_pl2, n_pl1, n_tmom, n_prev;
+    double n_tau, n_trial, n_gy, n_gd, n_cxx, n_pl2, n_pl1, n_tmom, n_prev, n_beta;
     bool do_update, obj_known, resolve_obj, ls_done, plain_copy, write_new_obj;
     double resolved_obj, beta, this_step, new_obj;
 };
@@ -145,7 +148,7 @@ __device__ __forceinline__ PgOut pg_decide(const PgIn& in, const double (&sums)[
     o.n_phase = in.phase; o.n_gmode = GM_SKIP; o.n_k = in.k; o.n_shrinks = in.shrinks;
     o.n_obj_pending = in.obj_pending; o.n_stop = in.stop_reason; o.n_ngrad = in.n_grad_calls;
     o.n_tau = in.tau; o.n_trial = in.trial_t; o.n_gy = in.gy; o.n_gd = in.gd; o.n_cxx = in.cand_xx;
-    o.n_pl2 = in.pend_l2; o.n_pl1 = in.pend_l1; o.n_tmom = in.t_mom; o.n_prev = in.prev_step;
+    o.n_pl2 = in.pend_l2; o.n_pl1 = in.pend_l1; o.n_tmom = in.t_mom; o.n_prev = in.prev_step; o.n_beta = in.beta_y;
     o.do_update = false; o.obj_known = false; o.resolve_obj = false; o.ls_done = false;
     o.plain_copy = false; o.write_new_obj = false;
     o.resolved_obj = 0.0; o.beta = 0.0; o.this_step = 0.0; o.new_obj = 0.0;
@@ -241,8 +244,11 @@ __device__ __forceinline__ PgOut pg_decide(const PgIn& in, const double (&sums)[
             o.n_gmode = o.n_obj_pending ? GM_DOT2 : GM_SKIP;
         } else {
             o.n_phase = PH_GRAD;
-            o.n_gmode = GM_GRAD | (o.n_obj_pending ? GM_DOT2 : 0);
+            // the next pass evaluates the gradient at the new y and, for the history, the residual norm of the
+            // iterate just accepted: from the recurrence (every pass keeps q current) or from a second dot
+            o.n_gmode = GM_GRAD | (in.use_qrec ? GM_QREC : (o.n_obj_pending ? GM_DOT2 : 0));
         }
+        o.n_beta = o.plain_copy ? 0.0 : o.beta;   // what y_{k+1} is formed with (elementwise 2)
     }
     return o;
 }
@@ -295,6 +301,7 @@ __device__ __forceinline__ void pg_apply_state(FosCtrl* C, PgOut o, bool comm_ok
     C->pend_l1 = o.n_pl1;
     C->t_mom = o.n_tmom;
     C->prev_step = o.n_prev;
+    C->beta_y = o.n_beta;
 }
 
 // ---- the one thread that owns the control block writes the new state and the history scalars

@@ -230,6 +230,43 @@ def test_persistent_solve_kernel_shapes(n, d, dtype, monkeypatch):
     des.close()
 
 
+def test_objective_from_the_residual_recurrence(monkeypatch):
+    """Fixed-step solves with history record 0.5 |A x_k - b|^2 from the row-wise residual recurrence
+    q_k = (r_y + beta q_{k-1}) / (1 + beta) (GM_QREC) instead of a second dot product per pass.  Against the
+    second-dot path (FOS_QREC=0) over 300 iterations -- the recurrence must not drift -- for fista, fista with
+    restarts (beta drops to 0 and the chain restarts), fista_delta (beta != 0 from the first update) and ista
+    (beta = 0 throughout); the iterates are bit-identical (the objective never feeds back)."""
+    from fastoptsolver_b200 import iterative_solvers as S
+    from fastoptsolver_b200 import operators as OPS
+    from fastoptsolver_b200.design import DeviceDesign
+    des = DeviceDesign.synthetic(60_000, 1024, seed=8, noise_std=1.0, rho1=0.8, rho2=0.9)
+    des.standardize()
+    a1 = 0.02 * des.lambda_max()
+    out = {}
+    for q in ("1", "0"):
+        monkeypatch.setenv("FOS_QREC", q)
+        res = []
+        np.random.seed(0)
+        res.append(S.fista(des, None, "elasticnet", a1, 0.1 * a1, max_iter=300, return_history=True))
+        np.random.seed(0)
+        res.append(S.fista(des, None, "lasso", a1, 0.0, max_iter=300, adaptive_restart=True, restart_threshold=0.95,
+                           return_history=True))
+        np.random.seed(0)
+        res.append(S.fista_delta(des, None, "lasso", a1, 0.0, 2.5, max_iter=300, return_history=True))
+        np.random.seed(0)
+        L = S.estimate_lipschitz(des)
+        g, grad_g, prox_h = OPS.ista_callables(des, None, a1, 0.0)
+        x, log = S.ista(np.zeros(1024), g, grad_g, prox_h, L, max_iter=100, return_history=True)
+        res.append((x, {"obj": list(S.last_run["ista_obj"])}))
+        out[q] = res
+    for (xa, ha), (xb, hb) in zip(out["1"], out["0"]):
+        assert xa.tobytes() == xb.tobytes()
+        oa, ob = np.asarray(ha["obj"]), np.asarray(hb["obj"])
+        assert oa.shape == ob.shape and len(oa) >= 100
+        assert np.max(np.abs(oa - ob) / np.abs(ob)) <= 1e-12
+    des.close()
+
+
 def _lda(des):
     import ctypes as C
     from fastoptsolver_b200 import _lib
