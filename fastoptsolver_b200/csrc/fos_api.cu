@@ -591,13 +591,19 @@ static int alloc_matrix(fos_design* h) {
 namespace {
 
 struct HostStager {
-    static constexpr int T = 16;                // most copy threads (FOS_UPLOAD_THREADS, default 8)
+    static constexpr int T = 16;                // most copy threads (FOS_UPLOAD_THREADS; default: hardware threads, 8..16)
     static constexpr int NSLOT = 2;             // pinned slots per thread (double buffer)
     static constexpr size_t SLOT = 8u << 20;    // bytes per slot
     static constexpr size_t MIN_BYTES = 128u << 20;  // below this a plain cudaMemcpyAsync is used
 
+    // default: one copy thread per hardware thread the process may use, between 8 and 16 (measured on a 16-core
+    // host, 32.8 GB pageable source: 8 threads 41 GB/s, 12: 43, 16: 45)
+    static int default_threads() {
+        const unsigned hc = std::thread::hardware_concurrency();
+        return std::max(8, std::min(T, hc ? static_cast<int>(hc) : 8));
+    }
     static int slot_threads() {
-        int n = 8;
+        int n = default_threads();
         if (const char* e = getenv("FOS_UPLOAD_THREADS")) n = std::max(8, std::min(T, atoi(e)));
         return n;
     }
@@ -633,7 +639,7 @@ struct HostStager {
     std::unique_lock<std::mutex> own;
 
     int device = 0;
-    int threads = 8;
+    int threads = default_threads();
     cudaStream_t stream[T] = {};
     cudaEvent_t slot_ev[T][NSLOT] = {};
     cudaEvent_t done_ev[T] = {};

@@ -23,10 +23,11 @@ ap.add_argument("--cols", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--calls", type=int, default=5)
 ap.add_argument("--keep-synthetic", action="store_true", help="keep the generator's design alive (as bench.py does)")
+ap.add_argument("--pageable", action="store_true", help="plain numpy arrays (threaded pinned-staging upload)")
 a = ap.parse_args()
 des = DeviceDesign.synthetic(a.rows, a.cols, np.float64, **bench.SCENARIO)
 alpha1 = 0.1 * des.lambda_max()
-A_h, b_h = bench.host_copy_of(des, True)
+A_h, b_h = bench.host_copy_of(des, not a.pageable)
 if not a.keep_synthetic:
     des.close()
 for i in range(a.calls):
