@@ -599,7 +599,9 @@ struct HostStager {
     // default: one copy thread per hardware thread the process may use, between 8 and 16 (measured on a 16-core
     // host, 32.8 GB pageable source: 8 threads 41 GB/s, 12: 43, 16: 45)
     static int default_threads() {
-        const unsigned hc = std::thread::hardware_concurrency();
+        unsigned hc = std::thread::hardware_concurrency();
+        // several ranks on one host (torchrun exports LOCAL_WORLD_SIZE) share the cores
+        if (const char* lw = getenv("LOCAL_WORLD_SIZE")) hc /= static_cast<unsigned>(std::max(1, atoi(lw)));
         return std::max(8, std::min(T, hc ? static_cast<int>(hc) : 8));
     }
     static int slot_threads() {
