@@ -1449,6 +1449,10 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
         // designs) the peer exchange; it leaves when the state machine reaches PH_DONE.  A refused
         // launch (the cooperative launch cannot place every CTA: SMs reserved by another context)
         // switches the design to the two-launch path for good.
+        // The persistent kernel holds every SM until the solve is over, and on a row-sharded design it waits
+        // for its peers: a collective of ANOTHER library enqueued earlier on another stream of this device
+        // (say an NCCL all-reduce the peers are already blocked in) must not end up queued behind it.
+        if (h->world > 1) cudaDeviceSynchronize();
         if (fos_launch_solve(h, hist, max_pairs) == FOS_OK) {
             pairs = 1;
         } else {
