@@ -1398,8 +1398,18 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
     c->armijo_c = p->armijo_c;
     // Fixed-step solves with history on streaming designs: the recorded objective's residual norm comes from
     // the row-wise residual recurrence (GM_QREC) instead of a second dot product in every pass (FOS_QREC=0: off)
+    // It trades 16 FP64 FMAs per 16 elements for ~40 cycles of latency per stage on one warp.  Which one costs
+    // more depends on the regime (measured, alternating A/B on the same box): a solve long enough to sit at the
+    // power cap gains (1M x 4096: 4.62 vs 5.11 ms per pass; 8 x 125k rows sustained: 1400 vs 1366 it/s), a short
+    // burst at full clocks loses (125k x 4096, 20 iterations = 13 ms: 0.645 vs 0.628 ms per pass).  Hence: on
+    // when the solve is expected to stream for >= 60 ms (max_iter passes at 6.5 TB/s); FOS_QREC=1 / 0 forces it.
     bool qrec = want_obj && !p->backtracking && h->kern_kind == 1 && K > 0;
-    if (const char* e = getenv("FOS_QREC")) qrec = qrec && e[0] != '0';
+    {
+        const double est_ms = static_cast<double>(K) * static_cast<double>(h->n) * h->lda * elem_size(h->dtype) / 6.5e9;
+        const char* e = getenv("FOS_QREC");
+        if (e && e[0] == '0') qrec = false;
+        else if (!(e && e[0] == '1')) qrec = qrec && est_ms >= 60.0;
+    }
     if (qrec && h->qres == nullptr &&
         fos_pool_malloc(reinterpret_cast<void**>(&h->qres), static_cast<size_t>(h->n) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();

@@ -143,6 +143,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     }
     double s1 = 0.0, s2 = 0.0;
     const double q_inv = QREC ? 1.0 / (1.0 + beta_y) : 1.0;
+    const bool q_here = QREC && (warp == NW - 1);
+    double q_nxt[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) q_nxt[r] = (QREC && q_here && beta_y != 0.0 && lo + r < hi) ? __ldcg(a.qres + lo + r) : 0.0;
 
     // b values of the next two stages, prefetched by lanes < R of both half-warps of warp 0 (each
     // half subtracts b from the dot it ends up holding, see the paired butterfly below)
@@ -164,11 +168,16 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         b_left -= R;
         const int rows = static_cast<int>(min(static_cast<long long>(R), hi - lo - static_cast<long long>(s) * R));
         const uint32_t st = ring_u32 + static_cast<uint32_t>(slot) * static_cast<uint32_t>(stage_bytes);
+        // (the LAST warp carries the recurrence: warp 0 already subtracts b and forms the residual sums, and the
+        // other warps wait for the slowest one at the next barrier; q_{k-1} is requested one stage ahead)
         double q_old[R];
-        if (QREC && warp == 0) {
+        if (QREC && q_here) {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                q_old[r] = (beta_y != 0.0 && r < rows) ? __ldcg(a.qres + lo + static_cast<long long>(s) * R + r) : 0.0;
+            for (int r = 0; r < R; ++r) {
+                q_old[r] = q_nxt[r];
+                const long long rn = lo + static_cast<long long>(s + 1) * R + r;
+                q_nxt[r] = (beta_y != 0.0 && rn < hi) ? __ldcg(a.qres + rn) : 0.0;
+            }
         }
 
         mbar_wait(&sm.full_bar[slot], parity);
@@ -300,11 +309,16 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 if (r < rows) {
                     if (GRAD) s1 = fma(r1[r], r1[r], s1);
                     if (DOT2) s2 = fma(r2[r], r2[r], s2);
-                    if (QREC) {
-                        const double qn = fma(beta_y, q_old[r], r1[r]) * q_inv;
-                        s2 = fma(qn, qn, s2);
-                        if (lane == 0) a.qres[lo + static_cast<long long>(s) * R + r] = qn;
-                    }
+                }
+            }
+        }
+        if (QREC && q_here) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < rows) {
+                    const double qn = fma(beta_y, q_old[r], r1[r]) * q_inv;
+                    s2 = fma(qn, qn, s2);
+                    if (lane == 0) a.qres[lo + static_cast<long long>(s) * R + r] = qn;
                 }
             }
         }
@@ -328,9 +342,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 if (c0 + e < a.ldv) *reinterpret_cast<double2*>(out + c0 + e) = make_double2(acc[j][e], acc[j][e + 1]);
         }
     }
+    if (QREC && tid == (NW - 1) * 32) a.partial_s[2 * cta + 1] = s2;
     if (tid == 0) {
         a.partial_s[2 * cta + 0] = s1;
-        a.partial_s[2 * cta + 1] = s2;
+        if (!QREC) a.partial_s[2 * cta + 1] = s2;
         if (a.cta_times) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

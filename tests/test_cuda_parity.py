@@ -131,6 +131,9 @@ def test_persistent_solve_kernel_and_two_launch_path(be, name, key, fused, monke
     traces of the reference, and the launch count says which one ran."""
     from fastoptsolver_b200 import iterative_solvers as S
     monkeypatch.setenv("FOS_FUSED", fused)
+    # the persistent-kernel runs also force the residual recurrence on (short solves default to the second dot):
+    # every fixed-step golden trace, objective trace included, through GM_QREC
+    monkeypatch.setenv("FOS_QREC", "1" if fused == "1" else "0")
     out, spec = harness.run_case(be, name, key)
     harness.check_case(out, spec, name, key, RTOL_F64)
     info = S.last_run["solver"]
