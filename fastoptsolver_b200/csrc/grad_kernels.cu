@@ -144,9 +144,13 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     double s1 = 0.0, s2 = 0.0;
     const double q_inv = QREC ? 1.0 / (1.0 + beta_y) : 1.0;
     const bool q_here = QREC && (warp == NW - 1);
-    double q_nxt[R];
+    double q_nxt[R], q_p[R], r_p[R];
+    int rows_p = 0;   // rows of the previous stage whose recurrence update is still pending
 #pragma unroll
-    for (int r = 0; r < R; ++r) q_nxt[r] = (QREC && q_here && beta_y != 0.0 && lo + r < hi) ? __ldcg(a.qres + lo + r) : 0.0;
+    for (int r = 0; r < R; ++r) {
+        q_nxt[r] = (QREC && q_here && beta_y != 0.0 && lo + r < hi) ? __ldcg(a.qres + lo + r) : 0.0;
+        q_p[r] = r_p[r] = 0.0;
+    }
 
     // b values of the next two stages, prefetched by lanes < R of both half-warps of warp 0 (each
     // half subtracts b from the dot it ends up holding, see the paired butterfly below)
@@ -172,6 +176,16 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         // other warps wait for the slowest one at the next barrier; q_{k-1} is requested one stage ahead)
         double q_old[R];
         if (QREC && q_here) {
+            // the update of the PREVIOUS stage's rows runs here, under this stage's barrier wait and loads: at the
+            // end of a stage it would sit on the path every warp waits for (40 cycles per stage, measured)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < rows_p) {
+                    const double qn = fma(beta_y, q_p[r], r_p[r]) * q_inv;
+                    s2 = fma(qn, qn, s2);
+                    if (lane == 0) a.qres[lo + static_cast<long long>(s - 1) * R + r] = qn;
+                }
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 q_old[r] = q_nxt[r];
@@ -315,12 +329,10 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         if (QREC && q_here) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (r < rows) {
-                    const double qn = fma(beta_y, q_old[r], r1[r]) * q_inv;
-                    s2 = fma(qn, qn, s2);
-                    if (lane == 0) a.qres[lo + static_cast<long long>(s) * R + r] = qn;
-                }
+                r_p[r] = r1[r];
+                q_p[r] = q_old[r];
             }
+            rows_p = rows;
         }
         b_cur = b_nxt;
         b_nxt = b_far;
@@ -330,6 +342,16 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
         }
     }
 
+    if (QREC && q_here) {   // the last stage's rows
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < rows_p) {
+                const double qn = fma(beta_y, q_p[r], r_p[r]) * q_inv;
+                s2 = fma(qn, qn, s2);
+                if (lane == 0) a.qres[lo + static_cast<long long>(nst - 1) * R + r] = qn;
+            }
+        }
+    }
     slot_io = slot;
     parity_io = parity;
     if (GRAD) {
