@@ -1411,7 +1411,7 @@ extern "C" int fos_prox_grad(fos_design* h, const fos_pg_params* p, fos_pg_resul
         else if (!(e && e[0] == '1')) qrec = qrec && est_ms >= 60.0;
     }
     if (qrec && h->qres == nullptr &&
-        fos_pool_malloc(reinterpret_cast<void**>(&h->qres), static_cast<size_t>(h->n) * sizeof(double)) != cudaSuccess) {
+        fos_pool_malloc(reinterpret_cast<void**>(&h->qres), 2 * static_cast<size_t>(h->n) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         h->qres = nullptr;
         qrec = false;

@@ -159,7 +159,7 @@ struct GradArgs {
     unsigned* slot_claim;           // [n_parts] pass number that last claimed each slot (with sm_slot)
     unsigned pass_no;               // number of this launch (monotonic per design): the claim token
     unsigned long long* cta_times;  // debug: [n_parts][2] start/end %globaltimer per CTA (nullable)
-    double* qres;                   // [n] residual A x_k - b of the current iterate, row by row (GM_QREC; nullable)
+    double* qres;                   // [2][n] residual A x_k - b of the iterate, row by row; the two copies alternate (GM_QREC; nullable)
 };
 
 // Everything the epilogue kernel needs.
@@ -224,7 +224,7 @@ struct fos_design {
     // gradient kernel selection (chosen at creation)
     int kern_kind = 0;  // 0 generic, 1 streaming
     FosGridSync* gsync = nullptr;  // persistent solve kernel (streaming designs only)
-    double* qres = nullptr;        // [n] residual vector of the recurrence (allocated by the first solve that uses it)
+    double* qres = nullptr;        // [2][n] residual vectors of the recurrence (allocated by the first solve that uses it)
     bool fused_ok = false;         // the whole solve may run as ONE launch of the persistent kernel
     bool lite_ok = false;         // a gradient-only kernel variant exists for this shape
     bool grad_only_hint = false;  // the running loop never asks for the second dot

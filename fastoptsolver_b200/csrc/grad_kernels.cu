@@ -119,7 +119,7 @@ template <typename T, int NT, int CPT, int R, bool GRAD, bool DOT2, bool WRAP = 
 __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT / 32, R>& sm,
                                                unsigned char* ring, int stage_bytes, int nstage,
                                                long long lo, long long hi, bool use_b, uint64_t pol, int cta,
-                                               int& slot_io, uint32_t& parity_io, double beta_y = 0.0) {
+                                               int& slot_io, uint32_t& parity_io, double beta_y = 0.0, int qsel = 0) {
     constexpr int VEC = Vec<T>::N;
     constexpr int NV = CPT / VEC;
     constexpr int NW = NT / 32;
@@ -144,11 +144,17 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
     double s1 = 0.0, s2 = 0.0;
     const double q_inv = QREC ? 1.0 / (1.0 + beta_y) : 1.0;
     const bool q_here = QREC && (warp == NW - 1);
+    // two copies of q, written and read in alternation from pass to pass: storing q_k(row i) and loading
+    // q_{k-1}(row i+2) of the SAME 32-byte sector in one stage made the load wait for the store (measured at
+    // 125k x 4096: CTA 0's streaming phase 575 -> 540 us per pass; the pass itself, set by the slowest CTA, did
+    // not move: 0.644 -> 0.648 ms)
+    double* const q_wr = QREC ? a.qres + static_cast<size_t>(qsel & 1) * static_cast<size_t>(a.n) : nullptr;
+    const double* const q_rd = QREC ? a.qres + static_cast<size_t>((qsel & 1) ^ 1) * static_cast<size_t>(a.n) : nullptr;
     double q_nxt[R], q_p[R], r_p[R];
     int rows_p = 0;   // rows of the previous stage whose recurrence update is still pending
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        q_nxt[r] = (QREC && q_here && beta_y != 0.0 && lo + r < hi) ? __ldcg(a.qres + lo + r) : 0.0;
+        q_nxt[r] = (QREC && q_here && beta_y != 0.0 && lo + r < hi) ? __ldcg(q_rd + lo + r) : 0.0;
         q_p[r] = r_p[r] = 0.0;
     }
 
@@ -183,14 +189,14 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
                 if (r < rows_p) {
                     const double qn = fma(beta_y, q_p[r], r_p[r]) * q_inv;
                     s2 = fma(qn, qn, s2);
-                    if (lane == 0) a.qres[lo + static_cast<long long>(s - 1) * R + r] = qn;
+                    if (lane == 0) q_wr[lo + static_cast<long long>(s - 1) * R + r] = qn;
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 q_old[r] = q_nxt[r];
                 const long long rn = lo + static_cast<long long>(s + 1) * R + r;
-                q_nxt[r] = (beta_y != 0.0 && rn < hi) ? __ldcg(a.qres + rn) : 0.0;
+                q_nxt[r] = (beta_y != 0.0 && rn < hi) ? __ldcg(q_rd + rn) : 0.0;
             }
         }
 
@@ -348,7 +354,7 @@ __device__ __forceinline__ void stream_consume(const GradArgs& a, StreamSmem<NT 
             if (r < rows_p) {
                 const double qn = fma(beta_y, q_p[r], r_p[r]) * q_inv;
                 s2 = fma(qn, qn, s2);
-                if (lane == 0) a.qres[lo + static_cast<long long>(nst - 1) * R + r] = qn;
+                if (lane == 0) q_wr[lo + static_cast<long long>(nst - 1) * R + r] = qn;
             }
         }
     }
@@ -485,7 +491,7 @@ grad_stream_kernel(const GradArgs a, int stage_bytes, int nstage) {
         case GM_GRAD:
             if ((mode & GM_QREC) && a.qres != nullptr)
                 stream_consume<T, NT, CPT, R, true, false, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol,
-                                                                        cta, slot0, par0, a.ctrl->beta_y);
+                                                                        cta, slot0, par0, a.ctrl->beta_y, a.ctrl->n_grad_calls);
             else
                 stream_consume<T, NT, CPT, R, true, false>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot0, par0);
             break;
@@ -697,7 +703,7 @@ solve_stream_kernel(const GradArgs a, const EpiArgs e, FosGridSync* gs, int stag
                 case GM_GRAD:
                     if ((mode & GM_QREC) && a.qres != nullptr)
                         stream_consume<T, NT, CPT, R, true, false, true, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol,
-                                                                               cta, slot, parity, ts.ctrl.beta_y);
+                                                                               cta, slot, parity, ts.ctrl.beta_y, ts.ctrl.n_grad_calls);
                     else
                         stream_consume<T, NT, CPT, R, true, false, true>(a, sm, ring, stage_bytes, nstage, lo, hi, use_b, pol, cta, slot, parity);
                     break;

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <chrono>
 
+#include <cuda.h>  // CUtensorMap (the encoder is resolved at run time, no link against libcuda)
+
 #include "fos_common.cuh"
 
 namespace {
@@ -133,6 +135,170 @@ __global__ void __launch_bounds__(256, 1) gram_syrk_kernel(const SyrkArgs g) {
             double2* dst = reinterpret_cast<double2*>(out + row * g.dpad + col);
             double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
             if (g.accumulate) {  // this (tile, split) slot belongs to this CTA alone; chunks are stream ordered
+                const double2 old = *dst;
+                v.x += old.x;
+                v.y += old.y;
+            }
+            *dst = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same tile product with the operands staged by the TMA unit (SASS: UTMALDG) instead of 8 LDGSTS per
+// thread and stage.  One elected lane issues 16 two-dimensional tensor copies per stage -- boxes of 16 columns
+// x 16 rows, SWIZZLE_128B; the eight warps take that turn round robin (a ninth, dedicated producer warp would
+// cap the kernel at 168 registers: three warps on one scheduler) -- and the warps never meet at a CTA barrier:
+// a stage is handed over by its `full` mbarrier (byte count) and returned by its `empty` mbarrier (one
+// arrival per warp).
+//   shared layout of one operand and stage: [8 column groups][16 rows][128 B], the 16-byte chunk c of row r stored
+//   at chunk c ^ (r % 8).  A DMMA step takes the four rows {0,1,4,5} + 2 (t & 1) + 8 (t >> 1) of the stage (the
+//   order of the k index inside a product is free as long as both operands use the same one): rows whose index
+//   differs in bit 2 land in the two halves of the 128-byte line, so every fragment load is the minimum of two
+//   wavefronts (tests/test_syrk_tma_layout_cpu.py replays the addressing).
+// Rows past the end of the split are zero-filled by the copy unit (tensor extent = rows of this call).
+// ------------------------------------------------------------------------------------------
+constexpr int TS_STAGES = 6;
+constexpr int TS_AHEAD = TS_STAGES - 2;  // stages requested ahead of the one being multiplied
+constexpr int TS_OP_BYTES = GKB * GT * 8;        // 16 KB: one operand of one stage
+constexpr int TS_STAGE_BYTES = 2 * TS_OP_BYTES;  // 32 KB
+constexpr int TS_BOX_BYTES = GKB * 16 * 8;       // 2 KB: one box
+constexpr int TS_SMEM_BYTES = TS_STAGES * TS_STAGE_BYTES + 2 * TS_STAGES * 8 + 1024;
+
+__device__ __forceinline__ void ts_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ts_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TS_DONE;\n\t"
+        "bra TS_WAIT;\n\t"
+        "TS_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// one box of the 2-D tensor (column, row) -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void ts_tma_2d(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(row), "r"(bar)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) gram_syrk_tma_kernel(const SyrkArgs g, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ unsigned char ts_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw = static_cast<uint32_t>(__cvta_generic_to_shared(ts_raw));
+    const uint32_t ring = (raw + 1023u) & ~1023u;  // SWIZZLE_128B repeats every 1024 bytes of shared address
+    const unsigned char* ring_p = ts_raw + (ring - raw);
+    const uint32_t full0 = ring + TS_STAGES * TS_STAGE_BYTES, empty0 = full0 + 8 * TS_STAGES;
+
+    const int split = blockIdx.x / g.ntiles;
+    int rem = blockIdx.x % g.ntiles, bi = 0;
+    while (rem >= g.nb - bi) {
+        rem -= g.nb - bi;
+        ++bi;
+    }
+    const int bj = bi + rem;
+    const long long k_lo = split * g.rows_per_split;
+    const long long k_hi = min(g.n, k_lo + g.rows_per_split);
+    const int nst = (k_hi > k_lo) ? static_cast<int>((k_hi - k_lo + GKB - 1) / GKB) : 0;
+
+    // request stage sp (one lane): its slot was last used by stage sp - TS_STAGES
+    auto produce = [&](int sp) {
+        if (sp < nst) {
+            const int slot = sp % TS_STAGES, turn = sp / TS_STAGES;
+            if (turn > 0) ts_mbar_wait(empty0 + 8 * slot, (turn - 1) & 1);
+            const uint32_t bar = full0 + 8 * slot;
+            ts_mbar_expect_tx(bar, TS_STAGE_BYTES);
+            const uint32_t dst = ring + slot * TS_STAGE_BYTES;
+            const int row = static_cast<int>(k_lo + static_cast<long long>(sp) * GKB);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ts_tma_2d(dst + q * TS_BOX_BYTES, &tmap, bi * GT + q * 16, row, bar);
+                ts_tma_2d(dst + TS_OP_BYTES + q * TS_BOX_BYTES, &tmap, bj * GT + q * 16, row, bar);
+            }
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < TS_STAGES; ++s) {
+            ts_mbar_init(full0 + 8 * s, 1);
+            ts_mbar_init(empty0 + 8 * s, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < TS_AHEAD; ++s) produce(s);
+    }
+    __syncthreads();
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int wi = warp >> 1, wj = warp & 1;  // 4 x 2 warps, warp tile 32 (i) x 64 (j)
+    const int fk = lane & 3, fc = lane >> 2;
+    // byte offset of this lane's element inside a box, for the two row quartets (t & 1) and the two 8-column
+    // halves of a box
+    int loff[2][2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int x = p * 2 + (fk & 1) + (fk >> 1) * 4;  // row % 8
+        const int y = (fc >> 1) ^ x;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) loff[p][hh] = x * 128 + ((y ^ (hh * 4)) * 16) + (fc & 1) * 8;
+    }
+    const int a_base = wi * 2 * TS_BOX_BYTES;                // column groups 2 wi .. 2 wi + 1 of operand I
+    const int b_base = TS_OP_BYTES + wj * 4 * TS_BOX_BYTES;  // column groups 4 wj .. 4 wj + 3 of operand J
+
+    for (int s = 0; s < nst; ++s) {
+        const int slot = s % TS_STAGES;
+        // the warps take turns as producer: stage s + TS_AHEAD goes into the slot of stage s - 2, which every
+        // warp has normally left long ago (the wait on its empty barrier then falls through)
+        if (warp == (s & 7) && lane == 0) produce(s + TS_AHEAD);
+        __syncwarp();
+        ts_mbar_wait(full0 + 8 * slot, (s / TS_STAGES) & 1);
+        const unsigned char* st = ring_p + static_cast<size_t>(slot) * TS_STAGE_BYTES;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                a[i] = *reinterpret_cast<const double*>(st + a_base + (i >> 1) * TS_BOX_BYTES + (t >> 1) * 1024 +
+                                                        loff[t & 1][i & 1]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                b[j] = *reinterpret_cast<const double*>(st + b_base + (j >> 1) * TS_BOX_BYTES + (t >> 1) * 1024 +
+                                                        loff[t & 1][j & 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) ts_mbar_arrive(empty0 + 8 * slot);
+    }
+
+    double* out = g.W + static_cast<size_t>(split) * g.dpad * g.dpad;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long row = static_cast<long long>(bi) * GT + wi * 32 + i * 8 + fc;
+            const long long col = static_cast<long long>(bj) * GT + wj * 64 + j * 8 + fk * 2;
+            double2* dst = reinterpret_cast<double2*>(out + row * g.dpad + col);
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (g.accumulate) {
                 const double2 old = *dst;
                 v.x += old.x;
                 v.y += old.y;
@@ -614,6 +780,55 @@ static void gram_free(fos_gram* g) {
 // ------------------------------------------------------------------------------------------
 static size_t syrk_smem_bytes() { return static_cast<size_t>(GSTAGES) * 2 * GKB * GLD * sizeof(double); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup
+typedef CUresult (*TsEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TsEncodeFn ts_encode_fn() {
+    static TsEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<TsEncodeFn>(p);
+    }();
+    return fn;
+}
+// A[rows][lda] as a 2-D tensor (columns innermost), boxes of 16 columns x GKB rows, 128-byte swizzle, zero fill
+static bool syrk_tensor_map(const SyrkArgs& a, CUtensorMap* m) {
+    TsEncodeFn fn = ts_encode_fn();
+    if (!fn || (a.lda & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) || a.n <= 0 || a.n > 0x7fffffffLL) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.lda), static_cast<cuuint64_t>(a.n)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.lda) * sizeof(double)};
+    const cuuint32_t box[2] = {16, GKB};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(a.A), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// tile products of one call: TMA-staged kernel, or the cp.async one (FOS_GRAM_TMA=0, odd pitch, no encoder)
+static std::atomic<long long> g_syrk_tma{0}, g_syrk_cp{0};
+static cudaError_t launch_syrk(const SyrkArgs& a, int nsplit, cudaStream_t s) {
+    const char* e = getenv("FOS_GRAM_TMA");
+    CUtensorMap m;
+    if (!(e && e[0] == '0') && syrk_tensor_map(a, &m)) {
+        cudaError_t st = cudaFuncSetAttribute(gram_syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+        if (st != cudaSuccess) return st;
+        gram_syrk_tma_kernel<<<dim3(a.ntiles * nsplit), dim3(256), TS_SMEM_BYTES, s>>>(a, m);
+        g_syrk_tma += 1;
+        return cudaGetLastError();
+    }
+    g_syrk_cp += 1;
+    cudaError_t st = cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(syrk_smem_bytes()));
+    if (st != cudaSuccess) return st;
+    gram_syrk_kernel<<<dim3(a.ntiles * nsplit), dim3(256), syrk_smem_bytes(), s>>>(a);
+    return cudaGetLastError();
+}
+
 static int syrk_pick_split(const fos_design* h, int ntiles, long long rows_avail, long long d) {
     int best = 1;
     double best_eff = 0.0;
@@ -721,6 +936,7 @@ int fos_upload_gram_begin(fos_design* h, cudaStream_t s) {
     const auto b1 = std::chrono::steady_clock::now();
     FOS_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(syrk_smem_bytes())));
+    FOS_CUDA(cudaFuncSetAttribute(gram_syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
     if (getenv("FOS_UPLOAD_DEBUG"))
         fprintf(stderr, "[fos] gram_begin: cudaMalloc(W %.0f MB + G) %.1f ms, func attribute %.1f ms\n", wbytes / 1e6,
                 std::chrono::duration<double, std::milli>(b1 - b0).count(),
@@ -742,8 +958,7 @@ int fos_upload_gram_chunk(fos_design* h, long long row0, long long rows, cudaStr
     a.accumulate = 1;
     long long rps = (rows + h->up_nsplit - 1) / h->up_nsplit;
     a.rows_per_split = (rps + GKB - 1) / GKB * GKB;
-    gram_syrk_kernel<<<dim3(a.ntiles * h->up_nsplit), dim3(256), syrk_smem_bytes(), s>>>(a);
-    FOS_CUDA(cudaGetLastError());
+    FOS_CUDA(launch_syrk(a, h->up_nsplit, s));
     h->launches += 1;
     return FOS_OK;
 }
@@ -928,12 +1143,9 @@ extern "C" int fos_gram_create(fos_design* h, fos_gram** out) {
         double* W = nullptr;
         FOS_CUDA(cudaMalloc(&W, static_cast<size_t>(best) * d * d * sizeof(double)));
         a.W = W;
-        const size_t smem = static_cast<size_t>(GSTAGES) * 2 * GKB * GLD * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
+        cudaEventRecord(g->ev0, g->stream);
+        cudaError_t e = launch_syrk(a, best, g->stream);
         if (e == cudaSuccess) {
-            cudaEventRecord(g->ev0, g->stream);
-            gram_syrk_kernel<<<dim3(a.ntiles * best), dim3(256), smem, g->stream>>>(a);
             gram_reduce_kernel<<<dim3(static_cast<unsigned>((d + 255) / 256), static_cast<unsigned>(d)), dim3(256), 0,
                                  g->stream>>>(W, g->G, d, best);
             cudaEventRecord(g->ev1, g->stream);
@@ -1053,6 +1265,12 @@ extern "C" int fos_gram_apply(fos_gram* g, const double* X, int n_cols, double* 
 extern "C" int fos_gram_set_btb(fos_gram* g, double btb) {
     FOS_REQUIRE(g, "null gram handle");
     g->bb = btb;
+    return FOS_OK;
+}
+
+extern "C" int fos_debug_gram_staging(long long* tma_launches, long long* cp_async_launches) {
+    if (tma_launches) *tma_launches = g_syrk_tma.load();
+    if (cp_async_launches) *cp_async_launches = g_syrk_cp.load();
     return FOS_OK;
 }
 

@@ -131,6 +131,35 @@ def test_warm_started_path_matches_cold_batch():
     des.close()
 
 
+def _staging_counts():
+    import ctypes as C
+    from fastoptsolver_b200 import _lib
+    t, c = C.c_longlong(0), C.c_longlong(0)
+    _lib.check(_lib.load().fos_debug_gram_staging(C.byref(t), C.byref(c)))
+    return t.value, c.value
+
+
+@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("n,d", [(4099, 384), (40, 128), (20011, 1024)])
+def test_tile_product_staging_variants(tma, n, d, monkeypatch):
+    """The tile products staged by the TMA unit (tensor maps, the default) and by cp.async (FOS_GRAM_TMA=0): the
+    variant asked for is the one that runs, both match numpy, ragged row counts are zero-filled."""
+    from fastoptsolver_b200.design import DeviceDesign
+    from fastoptsolver_b200.gram import GramDesign
+    monkeypatch.setenv("FOS_GRAM_TMA", tma)
+    A, b = _design(n, d, 3)
+    t0, c0 = _staging_counts()
+    des = DeviceDesign.from_host(A, b)
+    gram = GramDesign(des)
+    G, _ = gram.download()
+    t1, c1 = _staging_counts()
+    assert (t1 > t0, c1 > c0) == ((True, False) if tma == "1" else (False, True))
+    assert harness.rel_err(G, A.T @ A) <= 1e-13
+    assert np.array_equal(G, G.T)
+    gram.close()
+    des.close()
+
+
 def test_gram_and_path_at_config5_width():
     """d = 4096, 256 penalties -- the column count and penalty count of BASELINE config 5 (the
     7-split SYRK and the 128 x 64 path tiles at their real shape) on 20 000 rows: G, c, b.b against
