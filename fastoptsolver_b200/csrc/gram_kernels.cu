@@ -349,6 +349,7 @@ struct PathArgs {
     double alpha2, tau, beta;
     int d, Lpad;
     int mode;             // 0: FISTA step, 1: objective partials of X (Yin = X)
+    int ymap;             // which tensor map describes Yin (PathMaps::y[ymap]; TMA-staged kernels only)
     double* obj_part;     // [d/PM][Lpad][4]: x^T G x, c^T x, |x|_1, |x|^2 partials per i-block
     double* step_part;    // [d/PM][Lpad]: sum_i (x+ - x)^2 partials (nullable: not a check iteration)
 };
@@ -415,6 +416,104 @@ __device__ __forceinline__ void path_mainloop(const PathArgs& p, double* smem, i
     }
     cp_async_wait<0>();
     __syncthreads();   // the ring may be refilled by the next tile of the same CTA
+}
+
+// ---- the same contraction with both operands staged by the TMA unit (compare gram_syrk_tma_kernel) ----------
+// One box of PM rows x 16 k-values of G and one of TN rows x 16 k-values of Yin per stage, 128-byte swizzle: the
+// 16-byte chunk c of tile row r sits at chunk c ^ (r % 8) of the row's 128-byte line.  A fragment load reads the
+// eight rows r0 + fc at k = k4 + fk: chunk ((k4 >> 1) + (fk >> 1)) ^ fc, eight different chunks for the eight
+// rows, so the load is the minimum of two wavefronts without any padding.  The k order inside a product is the
+// cp.async kernel's: both stagings give the same bits.
+// The mbarrier phases run on across the calls of one CTA (stream-K: several segments), tracked in PathRing::gs.
+struct PathMaps {
+    CUtensorMap g;      // G as (k, i), box 16 x PM
+    CUtensorMap y[3];   // Y0, Y1, X as (k, l), box 16 x TN
+};
+struct PathRing {
+    uint32_t ring, full0, empty0;
+    const unsigned char* ring_p;
+    int gs;             // stages consumed so far by this CTA
+};
+template <int PM, int TN>
+struct PathTma {
+    static constexpr int STAGE_BYTES = (PM + TN) * 128;
+    static constexpr int STAGES = (PM + TN >= 256) ? 5 : 6;
+    static constexpr int AHEAD = STAGES - 2;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+};
+template <int PM, int TN>
+__device__ __forceinline__ void path_ring_init(PathRing& r, unsigned char* raw_p) {
+    using TM = PathTma<PM, TN>;
+    const uint32_t raw = static_cast<uint32_t>(__cvta_generic_to_shared(raw_p));
+    r.ring = (raw + 1023u) & ~1023u;
+    r.ring_p = raw_p + (r.ring - raw);
+    r.full0 = r.ring + TM::STAGES * TM::STAGE_BYTES;
+    r.empty0 = r.full0 + 8 * TM::STAGES;
+    r.gs = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TM::STAGES; ++s) {
+            ts_mbar_init(r.full0 + 8 * s, 1);
+            ts_mbar_init(r.empty0 + 8 * s, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+template <int PM, int TN = PN>
+__device__ __forceinline__ void path_mainloop_tma(const PathMaps& m, int ymap, PathRing& rg, int i0, int l0, int ks_lo,
+                                                  int nst, double (&acc)[4][PathTile<PM, TN>::NJ][2]) {
+    using PT = PathTile<PM, TN>;
+    using TM = PathTma<PM, TN>;
+    constexpr int WL = PT::WL, LW = PT::LW, NJ = PT::NJ;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gs0 = rg.gs;
+    auto produce = [&](int sl) {  // one lane: request stage sl of this call
+        if (sl < nst) {
+            const int g2 = gs0 + sl, slot = g2 % TM::STAGES, turn = g2 / TM::STAGES;
+            if (turn > 0) ts_mbar_wait(rg.empty0 + 8 * slot, (turn - 1) & 1);
+            const uint32_t bar = rg.full0 + 8 * slot;
+            ts_mbar_expect_tx(bar, TM::STAGE_BYTES);
+            const uint32_t dst = rg.ring + slot * TM::STAGE_BYTES;
+            const int k0 = (ks_lo + sl) * 16;
+            ts_tma_2d(dst, &m.g, k0, i0, bar);
+            ts_tma_2d(dst + PM * 128, &m.y[ymap], k0, l0, bar);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wi = warp / WL, wl = warp % WL;  // warp tile 32 (i) x LW (l)
+    const int fk = lane & 3, fc = lane >> 2;
+    int koff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) koff[q] = fc * 128 + ((((fk >> 1) + 2 * q) ^ fc) * 16) + (fk & 1) * 8;
+    const int a_base = wi * 32 * 128, b_base = PM * 128 + wl * LW * 128;
+
+    if (tid == 0)
+        for (int s = 0; s < TM::AHEAD; ++s) produce(s);
+    for (int s = 0; s < nst; ++s) {
+        const int g2 = gs0 + s, slot = g2 % TM::STAGES;
+        if (warp == (s & 7) && lane == 0) produce(s + TM::AHEAD);
+        __syncwarp();
+        ts_mbar_wait(rg.full0 + 8 * slot, (g2 / TM::STAGES) & 1);
+        const unsigned char* st = rg.ring_p + static_cast<size_t>(slot) * TM::STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double a[4], b[NJ];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double*>(st + a_base + i * 1024 + koff[q]);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double*>(st + b_base + j * 1024 + koff[q]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) ts_mbar_arrive(rg.empty0 + 8 * slot);
+    }
+    rg.gs = gs0 + nst;
 }
 
 // iblk: index of the tile's i-block (row of the partial-sum arrays)
@@ -504,13 +603,19 @@ __device__ __forceinline__ void path_epilogue(const PathArgs& p, int i0, int l0,
     }
 }
 
-template <int PM>
-__global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p) {
-    extern __shared__ __align__(16) double smem[];  // [PSTAGES][(PM+PN)][PLD]
+template <int PM, bool TMA>
+__global__ void __launch_bounds__(256, 1) path_step_kernel(const PathArgs p, const __grid_constant__ PathMaps maps) {
+    extern __shared__ __align__(16) double smem[];  // cp.async: [PSTAGES][(PM+PN)][PLD]; TMA: swizzled ring + mbarriers
     __shared__ double part[8][PathTile<PM>::LW][4];
     const int i0 = blockIdx.x * PM, l0 = blockIdx.y * PN;
     double acc[4][PathTile<PM>::NJ][2];
-    path_mainloop<PM>(p, smem, i0, l0, 0, p.d / PK, acc);
+    if constexpr (TMA) {
+        PathRing rg;
+        path_ring_init<PM, PN>(rg, reinterpret_cast<unsigned char*>(smem));
+        path_mainloop_tma<PM>(maps, p.ymap, rg, i0, l0, 0, p.d / 16, acc);
+    } else {
+        path_mainloop<PM>(p, smem, i0, l0, 0, p.d / PK, acc);
+    }
     path_epilogue<PM>(p, i0, l0, blockIdx.x, acc, part);
 }
 
@@ -537,8 +642,8 @@ __device__ __forceinline__ long long sk_begin(const PathSkArgs& a, int c) {
 // TN = 64 or 128 penalties per tile: 128 x 128 tiles (warp tile 32 x 64, 12 fragment loads per 32 MMAs, as in
 // the SYRK kernel) are the efficient shape, and with equal k-step ranges their small number (64 tiles at 256
 // penalties) no longer starves SMs
-template <int TN>
-__global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a) {
+template <int TN, bool TMA>
+__global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a, const __grid_constant__ PathMaps maps) {
     constexpr int PM = 128;
     constexpr int NJ = PathTile<PM, TN>::NJ;
     extern __shared__ __align__(16) double smem[];
@@ -547,6 +652,8 @@ __global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a
     const PathArgs& p = a.p;
     const int tid = threadIdx.x;
     const int c = blockIdx.x;
+    PathRing rg;
+    if constexpr (TMA) path_ring_init<PM, TN>(rg, reinterpret_cast<unsigned char*>(smem));
     const int nlb = p.Lpad / TN;                 // l-blocks; tile t = (iblk = t / nlb, lblk = t % nlb)
     const long long r0 = sk_begin(a, c), r1 = sk_begin(a, c + 1);
     double acc[4][NJ][2];
@@ -555,7 +662,8 @@ __global__ void __launch_bounds__(256, 1) path_step_sk_kernel(const PathSkArgs a
         const int k_lo = static_cast<int>(r - static_cast<long long>(t) * a.KT);
         const int k_hi = static_cast<int>(min(static_cast<long long>(a.KT), r1 - static_cast<long long>(t) * a.KT));
         const int iblk = t / nlb, i0 = iblk * PM, l0 = (t % nlb) * TN;
-        path_mainloop<PM, TN>(p, smem, i0, l0, k_lo, k_hi - k_lo, acc);
+        if constexpr (TMA) path_mainloop_tma<PM, TN>(maps, p.ymap, rg, i0, l0, k_lo, k_hi - k_lo, acc);
+        else path_mainloop<PM, TN>(p, smem, i0, l0, k_lo, k_hi - k_lo, acc);
         if (k_lo == 0 && k_hi == a.KT) {
             path_epilogue<PM, TN>(p, i0, l0, iblk, acc, part);
         } else {
@@ -810,7 +918,7 @@ static bool syrk_tensor_map(const SyrkArgs& a, CUtensorMap* m) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // tile products of one call: TMA-staged kernel, or the cp.async one (FOS_GRAM_TMA=0, odd pitch, no encoder)
-static std::atomic<long long> g_syrk_tma{0}, g_syrk_cp{0};
+static std::atomic<long long> g_syrk_tma{0}, g_syrk_cp{0}, g_path_tma{0}, g_path_cp{0};
 static cudaError_t launch_syrk(const SyrkArgs& a, int nsplit, cudaStream_t s) {
     const char* e = getenv("FOS_GRAM_TMA");
     CUtensorMap m;
@@ -1273,32 +1381,60 @@ extern "C" int fos_debug_gram_staging(long long* tma_launches, long long* cp_asy
     if (cp_async_launches) *cp_async_launches = g_syrk_cp.load();
     return FOS_OK;
 }
+extern "C" int fos_debug_path_staging(long long* tma_solves, long long* cp_async_solves) {
+    if (tma_solves) *tma_solves = g_path_tma.load();
+    if (cp_async_solves) *cp_async_solves = g_path_cp.load();
+    return FOS_OK;
+}
 
+// G and the three l x d matrices of a path solve as 2-D tensors (k innermost), boxes of 16 k-values x pm / tn rows
+static bool path_tensor_maps(PathMaps* m, const double* G, const double* Y0, const double* Y1, const double* X, int d,
+                             int Lpad, int pm, int tn) {
+    TsEncodeFn fn = ts_encode_fn();
+    if (!fn || PK != 16 || (d & 1)) return false;
+    auto enc = [&](CUtensorMap* t, const double* base, int rows, int box_rows) {
+        if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d) * sizeof(double)};
+        const cuuint32_t box[2] = {16, static_cast<cuuint32_t>(box_rows)};
+        const cuuint32_t estr[2] = {1, 1};
+        return fn(t, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    return enc(&m->g, G, d, pm) && enc(&m->y[0], Y0, Lpad, tn) && enc(&m->y[1], Y1, Lpad, tn) && enc(&m->y[2], X, Lpad, tn);
+}
+
+// maps != nullptr: operands staged by the TMA unit; nullptr: the cp.async ring
 template <int PM>
-static cudaError_t launch_path(const PathArgs& p, cudaStream_t st) {
+static cudaError_t launch_path(const PathArgs& p, const PathMaps* maps, cudaStream_t st) {
+    if (maps) {
+        constexpr int smem = PathTma<PM, PN>::SMEM_BYTES;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        path_step_kernel<PM, true><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p, *maps);
+        return cudaGetLastError();
+    }
     const size_t smem = static_cast<size_t>(PSTAGES) * (PM + PN) * PLD * sizeof(double);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    path_step_kernel<PM><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p);
+    path_step_kernel<PM, false><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p, PathMaps{});
     return cudaGetLastError();
 }
 
-// stream-K launch (128 x 64 tiles only); W and ticket are owned by the caller
+// stream-K launch (128-row tiles only); W and ticket are owned by the caller
 template <int TN>
-static cudaError_t launch_path_sk(const PathArgs& p, double* W, unsigned* ticket, int P, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(PSTAGES) * (128 + TN) * PLD * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+static cudaError_t launch_path_sk(const PathArgs& p, const PathMaps* maps, double* W, unsigned* ticket, int P,
+                                  cudaStream_t st) {
     PathSkArgs a;
     a.p = p;
     a.W = W;
@@ -1306,14 +1442,33 @@ static cudaError_t launch_path_sk(const PathArgs& p, double* W, unsigned* ticket
     a.T = (p.d / 128) * (p.Lpad / TN);
     a.KT = p.d / PK;
     a.P = P;
-    path_step_sk_kernel<TN><<<dim3(P), dim3(256), smem, st>>>(a);
+    if (maps) {
+        constexpr int smem = PathTma<128, TN>::SMEM_BYTES;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        path_step_sk_kernel<TN, true><<<dim3(P), dim3(256), smem, st>>>(a, *maps);
+        return cudaGetLastError();
+    }
+    const size_t smem = static_cast<size_t>(PSTAGES) * (128 + TN) * PLD * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    path_step_sk_kernel<TN, false><<<dim3(P), dim3(256), smem, st>>>(a, PathMaps{});
     return cudaGetLastError();
 }
 
-static cudaError_t launch_path_pm(int pm, const PathArgs& p, cudaStream_t st) {
-    if (pm == 128) return launch_path<128>(p, st);
-    if (pm == 64) return launch_path<64>(p, st);
-    return launch_path<32>(p, st);
+static cudaError_t launch_path_pm(int pm, const PathArgs& p, const PathMaps* maps, cudaStream_t st) {
+    if (pm == 128) return launch_path<128>(p, maps, st);
+    if (pm == 64) return launch_path<64>(p, maps, st);
+    return launch_path<32>(p, maps, st);
 }
 
 extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_path_result* pr) {
@@ -1377,6 +1532,15 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         std::vector<double> al(Lpad, 0.0);
         for (int l = 0; l < n_lambda; ++l) al[l] = pp->alphas1[l];
         FOS_CUDA(cudaMemcpyAsync(a1, al.data(), Lpad * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+        // operand staging: TMA tensor maps (FOS_PATH_TMA=0: the cp.async ring); same bits either way
+        PathMaps maps_store;
+        const PathMaps* maps = nullptr;
+        {
+            const char* e = getenv("FOS_PATH_TMA");
+            if (!(e && e[0] == '0') && path_tensor_maps(&maps_store, g->G, Y0, Y1, X, d, Lpad, pm, use_sk ? tn : PN))
+                maps = &maps_store;
+        }
+        (maps ? g_path_tma : g_path_cp) += 1;
         PathArgs p{};
         p.G = g->G;
         p.c = g->c;
@@ -1400,11 +1564,12 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
             p.mode = 0;
             p.Yin = (k & 1) ? Y1 : Y0;
             p.Yout = (k & 1) ? Y0 : Y1;
+            p.ymap = k & 1;
             const bool check = pp->tol > 0.0 && ((k + 1) % pp->check_every == 0);
             p.step_part = check ? spart : nullptr;
-            FOS_CUDA(!use_sk ? launch_path_pm(pm, p, g->stream)
-                             : (tn == 128 ? launch_path_sk<128>(p, skW, sk_ticket, sm_count, g->stream)
-                                          : launch_path_sk<PN>(p, skW, sk_ticket, sm_count, g->stream)));
+            FOS_CUDA(!use_sk ? launch_path_pm(pm, p, maps, g->stream)
+                             : (tn == 128 ? launch_path_sk<128>(p, maps, skW, sk_ticket, sm_count, g->stream)
+                                          : launch_path_sk<PN>(p, maps, skW, sk_ticket, sm_count, g->stream)));
             ++n_launch;
             ++iters;
             if (check) {
@@ -1420,11 +1585,12 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         FOS_CUDA(cudaEventRecord(g->ev1, g->stream));
         p.mode = 1;
         p.Yin = X;
+        p.ymap = 2;
         p.Yout = nullptr;
         p.step_part = nullptr;
-        FOS_CUDA(!use_sk ? launch_path_pm(pm, p, g->stream)
-                             : (tn == 128 ? launch_path_sk<128>(p, skW, sk_ticket, sm_count, g->stream)
-                                          : launch_path_sk<PN>(p, skW, sk_ticket, sm_count, g->stream)));
+        FOS_CUDA(!use_sk ? launch_path_pm(pm, p, maps, g->stream)
+                         : (tn == 128 ? launch_path_sk<128>(p, maps, skW, sk_ticket, sm_count, g->stream)
+                                      : launch_path_sk<PN>(p, maps, skW, sk_ticket, sm_count, g->stream)));
         path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, nblk, Lpad, a1, pp->alpha2,
                                                                                    0.5 * g->bb, obj);
         n_launch += 2;

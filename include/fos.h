@@ -285,6 +285,9 @@ int fos_gram_set_btb(fos_gram* g, double btb);
 /* Debug: how many tile-product (SYRK) launches of this process were staged by the TMA unit (tensor maps, SASS UTMALDG)
  * and how many by the cp.async kernel (FOS_GRAM_TMA=0, an odd row pitch, or no tensor-map encoder in the driver). */
 int fos_debug_gram_staging(long long* tma_launches, long long* cp_async_launches);
+/* Debug: the same count for fos_gram_path_fista calls (FOS_PATH_TMA=0 selects the cp.async ring; results are
+ * bit-identical between the two). */
+int fos_debug_path_staging(long long* tma_solves, long long* cp_async_solves);
 /* Strong-rule screening on the regularisation path (the per-column
  * semantics stay those of fista, iterative_solvers.py:199-221).
  * fos_gram_subset: the Gram system restricted to the strictly increasing feature indices idx[0..n_idx):

@@ -160,6 +160,42 @@ def test_tile_product_staging_variants(tma, n, d, monkeypatch):
     des.close()
 
 
+def _path_staging_counts():
+    import ctypes as C
+    from fastoptsolver_b200 import _lib
+    t, c = C.c_longlong(0), C.c_longlong(0)
+    _lib.check(_lib.load().fos_debug_path_staging(C.byref(t), C.byref(c)))
+    return t.value, c.value
+
+
+@pytest.mark.parametrize("d,n_lambda,sk", [(384, 64, "0"), (256, 200, "0"), (128, 16, "0"), (1024, 192, "1"), (1024, 256, "1")])
+def test_path_operand_staging_variants_give_the_same_bits(d, n_lambda, sk, monkeypatch):
+    """The batched path iteration with its operands staged by the TMA unit (default) and by cp.async
+    (FOS_PATH_TMA=0), on the tile schedule (32/64/128-row tiles) and the stream-K schedule (64- and 128-penalty
+    tiles): the k order inside every product is the same, so X and the objectives agree bit for bit."""
+    from fastoptsolver_b200 import gram as GM
+    from fastoptsolver_b200.design import DeviceDesign
+    A, b = _design(3000, d, 5)
+    des = DeviceDesign.from_host(A, b)
+    gram = GM.GramDesign(des)
+    G, c = gram.download()
+    L = float(np.linalg.eigvalsh(G)[-1]) * 1.0001
+    alphas = float(np.max(np.abs(c))) * np.logspace(0, -2, n_lambda)
+    monkeypatch.setenv("FOS_PATH_SK", sk)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("FOS_PATH_TMA", tma)
+        t0, c0 = _path_staging_counts()
+        X, info = GM.fista_path(des, None, alphas, max_iter=25, L=L, gram=gram)
+        t1, c1 = _path_staging_counts()
+        assert (t1 - t0, c1 - c0) == ((1, 0) if tma == "1" else (0, 1))
+        out[tma] = (X.copy(), np.asarray(info["obj"]).copy())
+    assert out["1"][0].tobytes() == out["0"][0].tobytes()
+    assert out["1"][1].tobytes() == out["0"][1].tobytes()
+    gram.close()
+    des.close()
+
+
 def test_gram_and_path_at_config5_width():
     """d = 4096, 256 penalties -- the column count and penalty count of BASELINE config 5 (the
     7-split SYRK and the 128 x 64 path tiles at their real shape) on 20 000 rows: G, c, b.b against

@@ -48,3 +48,26 @@ def test_fragment_loads_undo_the_swizzle_and_are_two_wavefronts():
 def test_every_row_of_a_stage_is_taken_once():
     rows = sorted(_lane_offset(fk, t, 0)[1] for t in range(4) for fk in range(4))
     assert rows == list(range(GKB))
+
+
+def test_path_tile_fragment_loads():
+    """path_mainloop_tma: boxes of PM (or TN) rows x 16 k-values, one 128-byte line per tile row; a fragment load takes
+    the eight rows r0 + fc at k = 4 q + fk."""
+    rows = 32
+    T = np.random.default_rng(1).standard_normal((rows, 16))
+    sm = np.full(rows * 16, np.nan)
+    for r in range(rows):
+        for c in range(8):
+            for e in range(2):
+                sm[(r * 128 + ((c ^ (r % 8)) * 16) + e * 8) // 8] = T[r, c * 2 + e]
+    assert not np.isnan(sm).any()
+    for r0 in range(0, rows, 8):
+        for q in range(4):
+            slots = []
+            for lane in range(32):
+                fk, fc = lane & 3, lane >> 2
+                koff = fc * 128 + ((((fk >> 1) + 2 * q) ^ fc) * 16) + (fk & 1) * 8   # the kernel's koff[q]
+                byte = r0 * 128 + koff
+                assert sm[byte // 8] == T[r0 + fc, 4 * q + fk]
+                slots.append((byte % 128) // 8)
+            assert max(slots.count(s) for s in set(slots)) == 2
