@@ -10,7 +10,8 @@
 //                      Y+ = X+ + beta (X+ - X)          (iterative_solvers.py:173-221, batched)
 //   path_obj_kernel    per-column  0.5 x^T G x - c^T x + 0.5 b^T b (+0.5 a2 |x|^2) (+a1 |x|_1)
 //
-// Operands are staged with cp.async (16 B, L1 bypass) into a 4-stage shared-memory ring whose
+// Operands are staged by the TMA unit (2-D tensor maps, 128-byte swizzle, mbarrier hand-over; the default) or with
+// cp.async (16 B, L1 bypass; FOS_GRAM_TMA=0 / FOS_PATH_TMA=0) into a 4-stage shared-memory ring whose
 // row pitch is padded by 4 doubles, which makes every DMMA fragment load conflict free.
 // Bound: the fp64 tensor pipe (n d^2 FMA for the build, d^2 Lambda per path iteration).
 #include <math.h>

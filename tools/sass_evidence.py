@@ -16,7 +16,8 @@ SO = os.path.join(ROOT, "fastoptsolver_b200", "libfos_b200.so")
 WANT = {
     "sass_grad_stream.txt": [r"solve_stream_kernelIdLi256ELi16ELi1", r"grad_stream_kernelIdLi256ELi16ELi1ELb0ELb0",
                              r"solve_stream_kernelIfLi256ELi16ELi2", r"15epilogue_kernel"],
-    "sass_gram.txt": [r"gram_syrk_kernel", r"path_step_kernelILi128", r"gram_matvec_kernel", r"mrhs_stream_kernel"],
+    "sass_gram.txt": [r"gram_syrk_tma_kernel", r"gram_syrk_kernel", r"path_step_sk_kernelILi128ELb1", r"path_step_kernelILi128ELb1",
+                      r"path_step_kernelILi128ELb0", r"gram_matvec_kernel", r"mrhs_stream_kernel"],
 }
 KEYS = ("UBLKCP", "UTMALDG", "SYNCS", "DMMA", "LDGSTS", "DFMA", "SHFL", "LDS", "BAR", "MEMBAR", "RED", "ATOM", ".SYS", "LDG", "STG",
         "UCGABAR", "ACQBULK", "CCTL", "ERRBAR", "NANOSLEEP")
