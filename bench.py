@@ -938,7 +938,7 @@ def bench_path(ctx):
     rows_local = des.shape[0]
     tiles = d // 128 if d % 128 == 0 else (d + 127) // 128
     syrk_flop = 2.0 * rows_local * d * d / 2 * (1 + 1.0 / tiles)        # upper tile triangle incl. diagonal tiles
-    it_flop = 2.0 * d * d * ((Lm + 63) // 64 * 64)
+    it_flop = 2.0 * d * d * Lm    # algorithmic: the penalties asked for, not the padded tile width
     it_ms = loop_ms / K
     achieved = it_flop / (it_ms * 1e-3) / 1e12
     out = {"metric": "path_batched_fista_iters_per_s", "value": K / (loop_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -954,9 +954,11 @@ def bench_path(ctx):
            "gram_build": {"ms": build_ms, "wall_s": build_wall, "tflops": syrk_flop / (build_ms * 1e-3) / 1e12,
                           "nsplit": gram.nsplit, "frac_of_nominal": syrk_flop / (build_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS},
            "nnz_first_last": [int(np.count_nonzero(X[0])), int(np.count_nonzero(X[-1]))],
-           "roofline": {"kernel": "path_step_kernel", "bound": "tensor", "achieved": achieved,
+           "roofline": {"kernel": "path_step_sk_kernel / path_step_kernel (stream-K or tile schedule, TMA-staged operands "
+                                  "unless FOS_PATH_TMA=0)", "bound": "tensor", "achieved": achieved,
                         "peak": FP64_TENSOR_PEAK_TFLOPS, "peak_source": "nominal B200 dense fp64 (DMMA) 40 TFLOP/s; "
-                        "MEASURED_PEAKS.json holds no fp64 figure", "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
+                        "MEASURED_PEAKS.json holds no fp64 figure (ncu: 36 TFLOP/s with the pipe 97.6 % busy in the Gram build, "
+                        "profiles/r2_gram_tma_syrk_path_sk_500kx4096_L256.txt)", "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
                         "traffic": None, "algorithmic_flops_per_launch": it_flop, "kernel_ms_avg": it_ms,
                         "launches_timed": K}}
     if clocks is not None:

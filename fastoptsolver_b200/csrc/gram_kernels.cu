@@ -1478,21 +1478,34 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
     FOS_REQUIRE(pp->check_every >= 1 || pp->tol <= 0.0, "check_every must be >= 1 when tol > 0");
     FOS_CUDA(cudaSetDevice(g->device));
     const int d = g->d, n_lambda = pp->n_lambda;
-    const int Lpad = (n_lambda + PN - 1) / PN * PN;
+    int Lpad = (n_lambda + PN - 1) / PN * PN;
     // i-tile: the largest that still gives every SM a tile
     int pm = 128;
     while (pm > 32 && static_cast<long long>(d / pm) * (Lpad / PN) < 120) pm /= 2;
-    // Stream-K over 128 x 64 tiles whenever the tile count does not fill the SMs in whole waves (FOS_PATH_SK=0/1
+    // Stream-K over 128-row tiles whenever the tile count does not fill the SMs in whole waves (FOS_PATH_SK=0/1
     // forces the choice): every SM gets the same number of k-steps whatever the number of penalties.
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device);
-    const long long tiles128 = static_cast<long long>(d / 128) * (Lpad / PN);
-    bool use_sk = d % 128 == 0 && tiles128 * (d / PK) >= 4LL * sm_count && tiles128 <= 4LL * sm_count;
+    auto sk_fits = [&](long long tiles) { return d % 128 == 0 && tiles * (d / PK) >= 4LL * sm_count && tiles <= 4LL * sm_count; };
+    bool use_sk = sk_fits(static_cast<long long>(d / 128) * (Lpad / PN));
     if (const char* e = getenv("FOS_PATH_SK")) use_sk = use_sk && e[0] != '0';
-    // 128-penalty tiles when that costs no extra padding (FOS_PATH_TN=64 forces the narrow tile)
+    // penalties per tile: 128 when that costs no extra padding; 32 when the last block of 64 would be at most half
+    // full and the list is short (the 32 penalties a rank holds of a 256-penalty path on 8 GPUs: half the
+    // contraction of a 64-wide tile); FOS_PATH_TN=32|64|128 forces a width that divides the padded count
     int tn = (use_sk && Lpad % 128 == 0) ? 128 : PN;
-    if (const char* e = getenv("FOS_PATH_TN")) tn = (atoi(e) == 128 && use_sk && Lpad % 128 == 0) ? 128 : PN;
+    const int Lpad32 = (n_lambda + 31) / 32 * 32;
+    bool tn32 = use_sk && Lpad32 < Lpad && Lpad32 <= 160 && sk_fits(static_cast<long long>(d / 128) * (Lpad32 / 32));
+    if (const char* e = getenv("FOS_PATH_TN")) {
+        const int want = atoi(e);
+        tn32 = tn32 && want == 32;
+        if (want != 32) tn = (want == 128 && use_sk && Lpad % 128 == 0) ? 128 : PN;
+    }
+    if (tn32) {
+        tn = 32;
+        Lpad = Lpad32;
+    }
     if (use_sk) pm = 128;
+    const long long n_tiles = static_cast<long long>(d / 128) * (Lpad / tn);   // stream-K tiles (ticket words)
     const int nblk = d / pm;
     const size_t mat = static_cast<size_t>(Lpad) * d;
     double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr,
@@ -1518,8 +1531,8 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         FOS_CUDA(fos_pool_malloc_host(reinterpret_cast<void**>(&smax_host), sizeof(double)));
         if (use_sk) {
             FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&skW), static_cast<size_t>(sm_count) * 2 * 128 * tn * sizeof(double)));
-            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&sk_ticket), static_cast<size_t>(tiles128) * sizeof(unsigned)));
-            FOS_CUDA(cudaMemsetAsync(sk_ticket, 0, static_cast<size_t>(tiles128) * sizeof(unsigned), g->stream));
+            FOS_CUDA(fos_pool_malloc(reinterpret_cast<void**>(&sk_ticket), static_cast<size_t>(n_tiles) * sizeof(unsigned)));
+            FOS_CUDA(cudaMemsetAsync(sk_ticket, 0, static_cast<size_t>(n_tiles) * sizeof(unsigned), g->stream));
         }
         FOS_CUDA(cudaMemsetAsync(Y0, 0, mat * sizeof(double), g->stream));
         FOS_CUDA(cudaMemsetAsync(Y1, 0, mat * sizeof(double), g->stream));
@@ -1542,6 +1555,12 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
                 maps = &maps_store;
         }
         (maps ? g_path_tma : g_path_cp) += 1;
+        auto launch_step = [&](const PathArgs& q) -> cudaError_t {
+            if (!use_sk) return launch_path_pm(pm, q, maps, g->stream);
+            if (tn == 128) return launch_path_sk<128>(q, maps, skW, sk_ticket, sm_count, g->stream);
+            if (tn == 32) return launch_path_sk<32>(q, maps, skW, sk_ticket, sm_count, g->stream);
+            return launch_path_sk<PN>(q, maps, skW, sk_ticket, sm_count, g->stream);
+        };
         PathArgs p{};
         p.G = g->G;
         p.c = g->c;
@@ -1568,9 +1587,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
             p.ymap = k & 1;
             const bool check = pp->tol > 0.0 && ((k + 1) % pp->check_every == 0);
             p.step_part = check ? spart : nullptr;
-            FOS_CUDA(!use_sk ? launch_path_pm(pm, p, maps, g->stream)
-                             : (tn == 128 ? launch_path_sk<128>(p, maps, skW, sk_ticket, sm_count, g->stream)
-                                          : launch_path_sk<PN>(p, maps, skW, sk_ticket, sm_count, g->stream)));
+            FOS_CUDA(launch_step(p));
             ++n_launch;
             ++iters;
             if (check) {
@@ -1589,9 +1606,7 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         p.ymap = 2;
         p.Yout = nullptr;
         p.step_part = nullptr;
-        FOS_CUDA(!use_sk ? launch_path_pm(pm, p, maps, g->stream)
-                         : (tn == 128 ? launch_path_sk<128>(p, maps, skW, sk_ticket, sm_count, g->stream)
-                                      : launch_path_sk<PN>(p, maps, skW, sk_ticket, sm_count, g->stream)));
+        FOS_CUDA(launch_step(p));
         path_obj_finish_kernel<<<dim3((Lpad + 127) / 128), dim3(128), 0, g->stream>>>(part, nblk, Lpad, a1, pp->alpha2,
                                                                                    0.5 * g->bb, obj);
         n_launch += 2;

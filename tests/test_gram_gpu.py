@@ -168,7 +168,7 @@ def _path_staging_counts():
     return t.value, c.value
 
 
-@pytest.mark.parametrize("d,n_lambda,sk", [(384, 64, "0"), (256, 200, "0"), (128, 16, "0"), (1024, 192, "1"), (1024, 256, "1")])
+@pytest.mark.parametrize("d,n_lambda,sk", [(384, 64, "0"), (256, 200, "0"), (128, 16, "0"), (1024, 192, "1"), (1024, 256, "1"), (2048, 32, "1")])
 def test_path_operand_staging_variants_give_the_same_bits(d, n_lambda, sk, monkeypatch):
     """The batched path iteration with its operands staged by the TMA unit (default) and by cp.async
     (FOS_PATH_TMA=0), on the tile schedule (32/64/128-row tiles) and the stream-K schedule (64- and 128-penalty
