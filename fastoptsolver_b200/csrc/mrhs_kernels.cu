@@ -40,7 +40,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int MR_CLUSTER = 4;    // CTAs per row block (column quarters)
+constexpr int MR_CLUSTER = 4;    // CTAs per row block (column quarters); d = 4096 may use 8 (column eighths), see fos_mrhs_fista
+constexpr int MR_CLMAX = 8;
 constexpr int MR_TILE = 8;       // rows per tile (the M of the first contraction, the K of the second)
 constexpr int MR_NB = 8;         // penalties per pass (the N of both contractions)
 constexpr int MR_PAD = 32;       // bytes added to the shared row pitch (8 words: conflict-free fragments)
@@ -103,7 +104,7 @@ struct MrhsSmem {
     uint64_t redbar[2];               // all 8 warps stored their partial U of a tile
     uint64_t ubar[MR_UBUF];           // the CTA partials of all 4 cluster CTAs arrived (st.async bytes)
     double red[2][8][64];             // [parity][warp][row*8 + lambda] warp partials of U
-    double clu[MR_UBUF][MR_CLUSTER][64];  // [buffer][source CTA][row*8 + lambda], written by st.async from the peers
+    double clu[MR_UBUF][MR_CLMAX][64];  // [buffer][source CTA][row*8 + lambda], written by st.async from the peers
 };
 
 __device__ __forceinline__ void mr_mbar_arrive(uint64_t* bar) {
@@ -126,8 +127,8 @@ __device__ __forceinline__ void mr_st_async(uint32_t remote_addr, double v, uint
 // requests the next tile); warps 0-7 run   contract1(t+1) -> [warps 0,1: publish(t+1)] -> contract2(t)
 // and meet only through mbarriers: redbar (warp partials complete), ubar (the 4 CTA partials arrived
 // from the cluster, counted in bytes by st.async), empty (slot reusable).
-template <int CW>
-__global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS, 1) mrhs_stream_kernel(const MrhsArgs a) {
+template <int CW, int CL = MR_CLUSTER>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(MR_THREADS, 1) mrhs_stream_kernel(const MrhsArgs a) {
     constexpr int KS = CW / 4;   // k-steps of the first contraction per warp
     constexpr int MB = CW / 8;   // column blocks of the second contraction per warp
     constexpr int NCH = (KS >= 16) ? 16 : 8;  // independent accumulation chains of the first contraction
@@ -137,10 +138,10 @@ __global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fk = lane & 3, fc = lane >> 2;
     const int q = static_cast<int>(cluster.block_rank());      // column quarter
-    const int cl = blockIdx.x / MR_CLUSTER;                    // row block
+    const int cl = blockIdx.x / CL;                            // row block
     const long long lo = a.row_lo[cl], hi = a.row_lo[cl + 1];
     const int ntile = static_cast<int>((hi - lo + MR_TILE - 1) / MR_TILE);
-    const int dq = a.d / MR_CLUSTER;
+    const int dq = a.d / CL;
     const uint32_t row_bytes = static_cast<uint32_t>(dq) * 8u;
 
     if (tid == 0) {
@@ -239,7 +240,7 @@ __global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS,
         auto publish = [&](int t) {
             mr_mbar_wait(&sm.redbar[t & 1], static_cast<uint32_t>(t >> 1) & 1u);
             const int buf = t % MR_UBUF;
-            if (tid == 0) mr_mbar_expect_tx(&sm.ubar[buf], MR_CLUSTER * 64 * 8);
+            if (tid == 0) mr_mbar_expect_tx(&sm.ubar[buf], CL * 64 * 8);
             double v = sm.red[t & 1][0][tid];
 #pragma unroll
             for (int w = 1; w < 8; ++w) v += sm.red[t & 1][w][tid];
@@ -248,9 +249,9 @@ __global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS,
                 const long long row = lo + static_cast<long long>(t + 1) * MR_TILE + (tid >> 3);
                 b_pref = (row < hi) ? __ldg(a.b + row) : 0.0;
             }
-            const uint32_t off = static_cast<uint32_t>(((buf * MR_CLUSTER + q) * 64 + tid) * 8);
+            const uint32_t off = static_cast<uint32_t>(((buf * MR_CLMAX + q) * 64 + tid) * 8);
 #pragma unroll
-            for (int r = 0; r < MR_CLUSTER; ++r)
+            for (int r = 0; r < CL; ++r)
                 mr_st_async(mr_mapa(clu_base + off, r), v, mr_mapa(ubar_base + buf * 8, r));
         };
         // second contraction of tile t: R = sum_q (U_q [- b]) in rank order, accumulators += A_tile^T R
@@ -264,7 +265,7 @@ __global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(MR_THREADS,
                 const int i0 = fk * 8 + fc, i1 = (fk + 4) * 8 + fc;
                 double s0 = sm.clu[buf][0][i0], s1 = sm.clu[buf][0][i1];
 #pragma unroll
-                for (int r = 1; r < MR_CLUSTER; ++r) {
+                for (int r = 1; r < CL; ++r) {
                     s0 += sm.clu[buf][r][i0];
                     s1 += sm.clu[buf][r][i1];
                 }
@@ -400,7 +401,8 @@ __global__ void mrhs_step_finish_kernel(const double* __restrict__ part, int nbl
     }
 }
 
-const void* mrhs_kernel_for(int cw) {
+const void* mrhs_kernel_for(int cw, int cl) {
+    if (cl == 8) return (cw == 64) ? reinterpret_cast<const void*>(&mrhs_stream_kernel<64, 8>) : nullptr;
     switch (cw) {
         case 128: return reinterpret_cast<const void*>(&mrhs_stream_kernel<128>);
         case 64: return reinterpret_cast<const void*>(&mrhs_stream_kernel<64>);
@@ -424,18 +426,61 @@ extern "C" int fos_mrhs_fista(fos_design* h, const fos_path_params* pp, fos_path
         return FOS_ERR_UNSUPPORTED;
     }
     FOS_CUDA(cudaSetDevice(h->device));
-    const int d = h->d, ldv = h->ldv, CW = d / 32;
-    const int ncl = std::max(1, h->sm_count / MR_CLUSTER);
+    const int d = h->d, ldv = h->ldv;
+    // CTAs per row block.  At d = 4096 a cluster of 4 leaves room for three 64 KB tiles only, and since a tile's slot is
+    // free only after its SECOND contraction, one tile is in flight per CTA: the pass runs at the load latency
+    // (5.7 ms at 500k rows).  A cluster of 8 halves the tile (six 32 KB slots, four in flight) at the price of SM
+    // coverage (as many clusters of 8 as are co-resident, 16 on this part = 128 of 148 SMs): 5.0 ms, measured, so
+    // d = 4096 uses it; FOS_MRHS_CLUSTER=4 forces quarters.
     const int n_lambda = pp->n_lambda;
     const int nbatch = (n_lambda + MR_NB - 1) / MR_NB;
     const int Lpad = nbatch * MR_NB;
-    const void* fn = mrhs_kernel_for(CW);
-    const int dq = d / MR_CLUSTER;
-    const int pitch = dq * 8 + MR_PAD;
-    const int stage_bytes = (MR_TILE * pitch + 127) & ~127;
-    const int nstage = std::min(MR_MAXST, (200 * 1024) / stage_bytes);
-    FOS_REQUIRE(nstage >= 2, "row too wide for the multi-RHS ring");
-    FOS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, nstage * stage_bytes));
+    int CL = MR_CLUSTER, CW = 0, dq = 0, pitch = 0, stage_bytes = 0, nstage = 0, ncl = 0;
+    const void* fn = nullptr;
+    auto plan = [&](int cl_want) -> int {
+        CL = cl_want;
+        CW = d / CL / 8;
+        fn = mrhs_kernel_for(CW, CL);
+        FOS_REQUIRE(fn != nullptr, "no multi-RHS kernel for d = %d with clusters of %d", d, CL);
+        dq = d / CL;
+        pitch = dq * 8 + MR_PAD;
+        stage_bytes = (MR_TILE * pitch + 127) & ~127;
+        nstage = std::min(MR_MAXST, (200 * 1024) / stage_bytes);
+        FOS_REQUIRE(nstage >= 2, "row too wide for the multi-RHS ring");
+        FOS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, nstage * stage_bytes));
+        ncl = std::max(1, h->sm_count / CL);
+        if (CL > MR_CLUSTER) {
+            // every cluster must be resident at once: a second wave would double the pass
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(ncl * CL);
+            cfg.blockDim = dim3(MR_THREADS);
+            cfg.dynamicSmemBytes = static_cast<size_t>(nstage) * stage_bytes;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                max_clusters = 0;
+            }
+            if (max_clusters < 8) return FOS_ERR_UNSUPPORTED;   // not placeable / not worth it: the caller falls back
+            ncl = std::min(ncl, max_clusters);
+        }
+        return FOS_OK;
+    };
+    {
+        int want = (d == 4096) ? 8 : MR_CLUSTER;
+        if (const char* e = getenv("FOS_MRHS_CLUSTER")) {
+            if (atoi(e) == 4) want = MR_CLUSTER;
+        }
+        int st = plan(want);
+        if (st == FOS_ERR_UNSUPPORTED && want != MR_CLUSTER) st = plan(MR_CLUSTER);
+        FOS_TRY(st);
+    }
 
     // row blocks: multiples of MR_TILE rows, the last cluster takes the tail
     std::vector<long long> row_lo(ncl + 1);
@@ -496,7 +541,7 @@ extern "C" int fos_mrhs_fista(fos_design* h, const fos_path_params* pp, fos_path
             ma.Y = Yb;
             ma.grad = grad;
             void* params[1] = {&ma};
-            FOS_CUDA(fos_launch_ex(fn, dim3(ncl * MR_CLUSTER), dim3(MR_THREADS), static_cast<size_t>(nstage) * stage_bytes, s, params,
+            FOS_CUDA(fos_launch_ex(fn, dim3(ncl * CL), dim3(MR_THREADS), static_cast<size_t>(nstage) * stage_bytes, s, params,
                                    false, 0));
             h->launches++;
             return FOS_OK;

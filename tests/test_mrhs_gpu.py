@@ -20,12 +20,15 @@ def _design(n, d, seed):
     return A, b
 
 
-@pytest.mark.parametrize("n,d,n_lambda", [(6000, 1024, 11), (3001, 2048, 8), (2500, 4096, 3)])
-def test_every_column_matches_reference_fista(n, d, n_lambda):
+@pytest.mark.parametrize("n,d,n_lambda,cluster", [(6000, 1024, 11, "4"), (3001, 2048, 8, "4"), (2500, 4096, 3, "4"),
+                                                  (2500, 4096, 3, "8"), (9001, 4096, 9, "8"), (9001, 4096, 9, "4")])
+def test_every_column_matches_reference_fista(n, d, n_lambda, cluster, monkeypatch):
     """Column l == fista(A, b, ..., alphas1[l], alpha2) of the reference (via the oracle) to 1e-10:
     iterates after a fixed iteration count and the objective; row counts that are not multiples of
-    the 8-row tile or of the 37 row blocks, a padded last batch (11 = 8 + 3 penalties)."""
+    the 8-row tile or of the 37 row blocks, a padded last batch (11 = 8 + 3 penalties); clusters of 4
+    (column quarters) and, at d = 4096, of 8 (column eighths, FOS_MRHS_CLUSTER)."""
     import oracle
+    monkeypatch.setenv("FOS_MRHS_CLUSTER", cluster)
     from fastoptsolver_b200 import gram as GM
     from fastoptsolver_b200.design import DeviceDesign
     A, b = _design(n, d, 3)
