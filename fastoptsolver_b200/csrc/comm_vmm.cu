@@ -61,8 +61,6 @@ const Drv& drv() {
     return d;
 }
 
-size_t window_doubles(const fos_design* h) { return 2 * static_cast<size_t>(h->ldv + FOS_WIN_PAD); }
-
 #define FOS_DRV(expr)                                                                       \
     do {                                                                                    \
         CUresult _r = (expr);                                                               \

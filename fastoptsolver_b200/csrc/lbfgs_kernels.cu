@@ -202,7 +202,7 @@ __device__ void dcsrch_start(LsState& s, double stp, double f, double g, double 
 
 // returns 0: evaluate at the new stp ("FG"), 1: converged, 2: warning (search ends, step accepted)
 __device__ int dcsrch_step(LsState& s, double& stp, double f, double g, double stpmin, double stpmax) {
-    const double ftol = 1e-3, gtol = 0.9, xtol = 0.1;
+    const double gtol = 0.9, xtol = 0.1;   // (ftol = 1e-3 is folded into s.gtest when the search starts)
     const double ftest = s.finit + stp * s.gtest;
     if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
     int task = 0;

@@ -79,8 +79,6 @@ __device__ __forceinline__ void mr_dmma(double& d0, double& d1, double a, double
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void mr_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void mr_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 struct MrhsArgs {
     const double* A;        // n x lda row-major fp64
@@ -337,7 +335,6 @@ struct MrhsUpdateArgs {
 
 // one thread per (column, penalty); the cluster partials are summed in cluster order
 __global__ void __launch_bounds__(256) mrhs_update_kernel(const MrhsUpdateArgs u) {
-    __shared__ double red[8][8];
     const int l = threadIdx.x >> 5;          // penalty = warp
     const int lane = threadIdx.x & 31;
     const int col = blockIdx.x * 32 + lane;
@@ -360,7 +357,6 @@ __global__ void __launch_bounds__(256) mrhs_update_kernel(const MrhsUpdateArgs u
         dx2 = fos_warp_sum(dx2);
         if (lane == 0) u.step_part[static_cast<size_t>(blockIdx.x) * MR_NB + l] = dx2;
     }
-    (void)red;
 }
 
 // objective of the 8 columns of X: 0.5 sum_c norms[c][l] (+0.5 a2 |x|^2) (+a1[l] |x|_1); one warp per penalty
