@@ -1,5 +1,18 @@
-import os, sys, ctypes as C, numpy as np
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python
+"""Phase profile of the persistent solve kernel (CTA 0's %globaltimer stamps, fos_debug_solve_profile): us per
+pass spent in the streaming loop, at each of the three grid barriers, in the slice sums, the peer exchange, the
+elementwise steps and the decision, for the three kinds of pass -- objective from the residual recurrence
+(qrec), from a second dot product (dot2), gradient only (none).
+
+    python tools/exp_solve_phases.py [rows=125000]        # FOS_BALANCE=1: rate-weighted row blocks
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fastoptsolver_b200 import _lib, iterative_solvers as S
 from fastoptsolver_b200.design import DeviceDesign
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 125000
