@@ -1427,28 +1427,34 @@ static bool path_tensor_maps(PathMaps* m, const double* G, const double* Y0, con
     return enc(&m->g, G, d, pm) && enc(&m->y[0], Y0, Lpad, tn) && enc(&m->y[1], Y1, Lpad, tn) && enc(&m->y[2], X, Lpad, tn);
 }
 
+// cudaFuncSetAttribute once per kernel AND device: the attribute lives in the device's context, and one process may
+// hold designs on several GPUs
+static cudaError_t set_smem_once(const void* fn, int bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 // maps != nullptr: operands staged by the TMA unit; nullptr: the cp.async ring
 template <int PM>
 static cudaError_t launch_path(const PathArgs& p, const PathMaps* maps, cudaStream_t st) {
     if (maps) {
         constexpr int smem = PathTma<PM, PN>::SMEM_BYTES;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static std::atomic<unsigned long long> configured{0};
+        cudaError_t e = set_smem_once(reinterpret_cast<const void*>(&path_step_kernel<PM, true>), smem, configured);
+        if (e != cudaSuccess) return e;
         path_step_kernel<PM, true><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p, *maps);
         return cudaGetLastError();
     }
     const size_t smem = static_cast<size_t>(PSTAGES) * (PM + PN) * PLD * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(path_step_kernel<PM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    cudaError_t e = set_smem_once(reinterpret_cast<const void*>(&path_step_kernel<PM, false>), static_cast<int>(smem), configured);
+    if (e != cudaSuccess) return e;
     path_step_kernel<PM, false><<<dim3(p.d / PM, p.Lpad / PN), dim3(256), smem, st>>>(p, PathMaps{});
     return cudaGetLastError();
 }
@@ -1466,23 +1472,16 @@ static cudaError_t launch_path_sk(const PathArgs& p, const PathMaps* maps, doubl
     a.P = P;
     if (maps) {
         constexpr int smem = PathTma<128, TN>::SMEM_BYTES;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
+        static std::atomic<unsigned long long> attr_done{0};
+        cudaError_t e = set_smem_once(reinterpret_cast<const void*>(&path_step_sk_kernel<TN, true>), smem, attr_done);
+        if (e != cudaSuccess) return e;
         path_step_sk_kernel<TN, true><<<dim3(P), dim3(256), smem, st>>>(a, *maps);
         return cudaGetLastError();
     }
     const size_t smem = static_cast<size_t>(PSTAGES) * (128 + TN) * PLD * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(path_step_sk_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    cudaError_t e = set_smem_once(reinterpret_cast<const void*>(&path_step_sk_kernel<TN, false>), static_cast<int>(smem), attr_done);
+    if (e != cudaSuccess) return e;
     path_step_sk_kernel<TN, false><<<dim3(P), dim3(256), smem, st>>>(a, PathMaps{});
     return cudaGetLastError();
 }
