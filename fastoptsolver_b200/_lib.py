@@ -111,6 +111,7 @@ SIGNATURES = {
     "fos_debug_solve_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fos_debug_gram_staging": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fos_debug_path_staging": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fos_debug_path_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fos_design_solve_kernel_ok": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "fos_design_solve_kernel_disable": (C.c_int, [C.c_void_p]),
     "fos_design_lambda_max": (C.c_int, [C.c_void_p, c_double_p]),

@@ -1492,20 +1492,21 @@ static cudaError_t launch_path_pm(int pm, const PathArgs& p, const PathMaps* map
     return launch_path<32>(p, maps, st);
 }
 
-extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_path_result* pr) {
-    FOS_REQUIRE(g && pp && pr && pp->alphas1, "null pointer argument");
-    FOS_REQUIRE(pp->n_lambda >= 1 && pp->max_iter >= 0 && pp->step > 0.0, "bad argument");
-    FOS_REQUIRE(pp->check_every >= 1 || pp->tol <= 0.0, "check_every must be >= 1 when tol > 0");
-    FOS_CUDA(cudaSetDevice(g->device));
-    const int d = g->d, n_lambda = pp->n_lambda;
+// Schedule and tile shape of the batched path iteration for d features and n_lambda penalties on a part with
+// sm_count SMs (pure host logic: fos_debug_path_plan exposes it to the CPU tests)
+struct PathPlan {
+    int Lpad;            // padded penalty count (rows of Y / X)
+    int pm, tn;          // tile: pm features x tn penalties (tile schedule: tn = PN)
+    bool use_sk;         // stream-K schedule (128-row tiles) instead of one tile per CTA
+    long long n_tiles;   // 128-row tiles of the stream-K schedule (ticket words)
+};
+static PathPlan path_plan(int d, int n_lambda, int sm_count) {
     int Lpad = (n_lambda + PN - 1) / PN * PN;
     // i-tile: the largest that still gives every SM a tile
     int pm = 128;
     while (pm > 32 && static_cast<long long>(d / pm) * (Lpad / PN) < 120) pm /= 2;
     // Stream-K over 128-row tiles whenever the tile count does not fill the SMs in whole waves (FOS_PATH_SK=0/1
     // forces the choice): every SM gets the same number of k-steps whatever the number of penalties.
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device);
     auto sk_fits = [&](long long tiles) { return d % 128 == 0 && tiles * (d / PK) >= 4LL * sm_count && tiles <= 4LL * sm_count; };
     bool use_sk = sk_fits(static_cast<long long>(d / 128) * (Lpad / PN));
     if (const char* e = getenv("FOS_PATH_SK")) use_sk = use_sk && e[0] != '0';
@@ -1525,7 +1526,39 @@ extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_p
         Lpad = Lpad32;
     }
     if (use_sk) pm = 128;
-    const long long n_tiles = static_cast<long long>(d / 128) * (Lpad / tn);   // stream-K tiles (ticket words)
+    PathPlan out;
+    out.Lpad = Lpad;
+    out.pm = pm;
+    out.tn = tn;
+    out.use_sk = use_sk;
+    out.n_tiles = static_cast<long long>(d / 128) * (Lpad / tn);
+    return out;
+}
+
+extern "C" int fos_debug_path_plan(int d, int n_lambda, int sm_count, int* padded_lambdas, int* tile_rows, int* tile_cols,
+                                   int* stream_k, long long* n_tiles) {
+    FOS_REQUIRE(d >= 128 && d % 128 == 0 && n_lambda >= 1 && sm_count >= 1, "bad argument");
+    const PathPlan pl = path_plan(d, n_lambda, sm_count);
+    if (padded_lambdas) *padded_lambdas = pl.Lpad;
+    if (tile_rows) *tile_rows = pl.pm;
+    if (tile_cols) *tile_cols = pl.tn;
+    if (stream_k) *stream_k = pl.use_sk ? 1 : 0;
+    if (n_tiles) *n_tiles = pl.n_tiles;
+    return FOS_OK;
+}
+
+extern "C" int fos_gram_path_fista(fos_gram* g, const fos_path_params* pp, fos_path_result* pr) {
+    FOS_REQUIRE(g && pp && pr && pp->alphas1, "null pointer argument");
+    FOS_REQUIRE(pp->n_lambda >= 1 && pp->max_iter >= 0 && pp->step > 0.0, "bad argument");
+    FOS_REQUIRE(pp->check_every >= 1 || pp->tol <= 0.0, "check_every must be >= 1 when tol > 0");
+    FOS_CUDA(cudaSetDevice(g->device));
+    const int d = g->d, n_lambda = pp->n_lambda;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device);
+    const PathPlan plan = path_plan(d, n_lambda, sm_count);
+    const int Lpad = plan.Lpad, pm = plan.pm, tn = plan.tn;
+    const bool use_sk = plan.use_sk;
+    const long long n_tiles = plan.n_tiles;
     const int nblk = d / pm;
     const size_t mat = static_cast<size_t>(Lpad) * d;
     double *Y0 = nullptr, *Y1 = nullptr, *X = nullptr, *a1 = nullptr, *part = nullptr, *obj = nullptr,

@@ -288,6 +288,11 @@ int fos_debug_gram_staging(long long* tma_launches, long long* cp_async_launches
 /* Debug: the same count for fos_gram_path_fista calls (FOS_PATH_TMA=0 selects the cp.async ring; results are
  * bit-identical between the two). */
 int fos_debug_path_staging(long long* tma_solves, long long* cp_async_solves);
+/* Host logic only (runs without a GPU): the schedule fos_gram_path_fista picks for d features (multiple of 128) and
+ * n_lambda penalties on a part with sm_count SMs -- padded penalty count, tile shape, stream-K or one tile per CTA,
+ * number of 128-row tiles.  Honours FOS_PATH_SK / FOS_PATH_TN like the solver does. */
+int fos_debug_path_plan(int d, int n_lambda, int sm_count, int* padded_lambdas, int* tile_rows, int* tile_cols,
+                        int* stream_k, long long* n_tiles);
 /* Strong-rule screening on the regularisation path (the per-column
  * semantics stay those of fista, iterative_solvers.py:199-221).
  * fos_gram_subset: the Gram system restricted to the strictly increasing feature indices idx[0..n_idx):
