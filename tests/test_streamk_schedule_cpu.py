@@ -42,6 +42,25 @@ def contributors(T, KT, P, t):
 @pytest.mark.parametrize("T,KT,P", [(128, 256, 148), (64, 256, 148), (32, 256, 148), (16, 64, 148), (32, 128, 148),
                                      (592, 256, 148), (5, 2048, 148), (33, 96, 148), (64, 256, 132), (7, 37, 148)])
 def test_schedule_covers_every_k_step_once_and_fixup_reads_the_right_slots(T, KT, P):
+    _check_schedule(T, KT, P)
+
+
+def test_schedule_properties_on_random_shapes():
+    """The same properties for random tile counts, k-step counts and CTA counts (hypothesis), including the
+    degenerate corners: one tile, one k-step per tile, more tiles than CTAs, a single CTA."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 260), st.integers(1, 160))
+    def run(T, KT, P):
+        if T * KT < P:
+            P = T * KT
+        _check_schedule(T, KT, P)
+
+    run()
+
+
+def _check_schedule(T, KT, P):
     assert T * KT >= P          # the host only picks the schedule then
     cover = {}
     slot_of = {}
